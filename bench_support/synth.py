@@ -19,7 +19,7 @@ TWO_PI = 2.0 * np.pi
 
 
 def mono_phase(t, chan_index, deviation):
-    """2*pi*dev*integral of 0.5*sin(2*pi*fm*t), fm = 300 + 50*c Hz."""
+    """Phase (radians) 2*pi*dev*integral of 0.5*sin(2*pi*fm*t), fm = 300 + 50*c Hz."""
     fm = 300.0 + 50.0 * (chan_index % 64)
     return (deviation * 0.5 / fm) * (1.0 - np.cos(TWO_PI * fm * t))
 
@@ -49,7 +49,7 @@ def station(n_samples, rate, chan_index, offset_hz=0.0, deviation=None, stereo=F
     if stereo:
         ph = stereo_phase(t, chan_index, deviation)
     else:
-        ph = TWO_PI * mono_phase(t, chan_index, deviation)
+        ph = mono_phase(t, chan_index, deviation)
     if phase0 is None:
         phase0 = 0.61803398875 * chan_index
     # carrier offset: exact modular phase to stay accurate at large offsets

@@ -1,0 +1,567 @@
+// rc_fft.cuh -- batched mixed-radix complex FFT for sm_100a (sizes 2^a 3^b 5^c).
+//
+// Why it exists: every stage of the reference's receive chain is a Fourier
+// operation on block sizes that are never powers of two -- Tuner.load is one
+// N-point FFT (reference radiocore/tools/tuner.py:137-138), Tuner.run an
+// inverse B-point FFT of gathered bins (tuner.py:159-161), Decimate an
+// rfft/irfft pair (radiocore/analog/decimate.py:48), PLL.step a Hilbert
+// transform (radiocore/analog/pll.py:34).  This header is the one FFT engine
+// all of them are built on.
+//
+// Design (B200-first, no tensor cores -- the work is butterflies on fp32 pairs):
+//   * A transform of length n is split into 1..3 "passes" n = R1*R2*R3.  A pass
+//     is a Stockham step with a large radix R (up to ~1500): input element
+//     (j, t) lives at j + t*(n/R), output element (j, K) at
+//     expand(j, Ns, R) + K*Ns, Ns = product of earlier R's -- so the data comes
+//     out in natural order without a transpose kernel.
+//   * One CTA owns a tile of T adjacent columns j (T = 16 -> every global access
+//     is a full 128-byte line) and all R rows; the T independent R-point FFTs
+//     run in shared memory (pitch T+1 -> conflict-free both along c and along K)
+//     as in-place decimation-in-time stages with radices {2,3,4,5,8,10,16,25}
+//     evaluated in registers.
+//   * Inter-pass twiddles W_{Ns*R}^{t*k} are generated per thread by an fp64
+//     recurrence seeded from two small fp64 tables (exact to ~1e-16), then
+//     rounded to fp32 once -- no sincos in the inner loop, no accuracy loss.
+//   * The first pass reads through a LoadOp functor and the last pass writes
+//     through a StoreOp functor, so gathers/windows/scales fuse into the FFT.
+//
+// Every per-thread phase is a __host__ __device__ function so the exact index
+// arithmetic can be replayed on the CPU (tests/native/emulate_fft.cu) -- the
+// build container has no GPU.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#ifndef RC_HD
+#define RC_HD __host__ __device__ __forceinline__
+#endif
+
+namespace rc {
+
+// ------------------------------------------------------------------ complex
+RC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+RC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+RC_HD float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+RC_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+RC_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+RC_HD double2 cmul64(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiply by SIGN*i (forward transform SIGN = -1  ->  times -i)
+template <int SIGN> RC_HD float2 mul_si(float2 a) {
+    return SIGN < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+
+template <typename T> RC_HD T ldg(const T* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// ------------------------------------------------- register-level butterflies
+template <int N> struct SmallTw;
+#include "rc_small_tw.inc"
+
+// v *= W_N^k (forward sign) or its conjugate; k, N compile-time after unrolling.
+template <int N, int SIGN> RC_HD float2 small_twiddle(float2 v, int k) {
+    k %= N;
+    if (k == 0) return v;
+    if (N % 4 == 0 && k == N / 4) return mul_si<SIGN>(v);
+    if (N % 2 == 0 && k == N / 2) return make_float2(-v.x, -v.y);
+    if (N % 4 == 0 && k == 3 * N / 4) return mul_si<-SIGN>(v);
+    return cmul(v, make_float2(SmallTw<N>::c(k), SIGN * SmallTw<N>::s(k)));
+}
+
+template <int R, int SIGN> struct Dft;
+
+template <int SIGN> struct Dft<2, SIGN> {
+    static RC_HD void run(float2* v) {
+        float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <int SIGN> struct Dft<3, SIGN> {
+    static RC_HD void run(float2* v) {
+        const float h = 0.86602540378443865f;   // sin(2 pi / 3)
+        float2 t1 = cadd(v[1], v[2]);
+        float2 t2 = csub(v[1], v[2]);
+        float2 m = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+        float2 r = mul_si<SIGN>(cscale(t2, h));  // SIGN*i*h*(v1-v2)
+        v[0] = cadd(v[0], t1);
+        v[1] = cadd(m, r);
+        v[2] = csub(m, r);
+    }
+};
+
+template <int SIGN> struct Dft<4, SIGN> {
+    static RC_HD void run(float2* v) {
+        float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+        float2 c = cadd(v[1], v[3]), d = mul_si<SIGN>(csub(v[1], v[3]));
+        v[0] = cadd(a, c);
+        v[1] = cadd(b, d);
+        v[2] = csub(a, c);
+        v[3] = csub(b, d);
+    }
+};
+
+template <int SIGN> struct Dft<5, SIGN> {
+    static RC_HD void run(float2* v) {
+        const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+        const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+        float2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
+        float2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+        float2 x0 = v[0];
+        v[0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
+        float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
+        float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
+        float2 q1 = mul_si<SIGN>(make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y));
+        float2 q2 = mul_si<SIGN>(make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y));
+        v[1] = cadd(p1, q1);
+        v[4] = csub(p1, q1);
+        v[2] = cadd(p2, q2);
+        v[3] = csub(p2, q2);
+    }
+};
+
+// Cooley-Tukey composite in registers: n = R2*n1 + n2, k = k1 + R1*k2.
+template <int R1, int R2, int SIGN> RC_HD void dft_composite(float2* v) {
+    constexpr int N = R1 * R2;
+    float2 t[N];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; n2++) {
+        float2 a[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; n1++) a[n1] = v[R2 * n1 + n2];
+        Dft<R1, SIGN>::run(a);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; k1++) t[k1 * R2 + n2] = small_twiddle<N, SIGN>(a[k1], n2 * k1);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; k1++) {
+        float2 b[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; n2++) b[n2] = t[k1 * R2 + n2];
+        Dft<R2, SIGN>::run(b);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) v[k1 + R1 * k2] = b[k2];
+    }
+}
+template <int SIGN> struct Dft<8, SIGN> { static RC_HD void run(float2* v) { dft_composite<2, 4, SIGN>(v); } };
+template <int SIGN> struct Dft<10, SIGN> { static RC_HD void run(float2* v) { dft_composite<2, 5, SIGN>(v); } };
+template <int SIGN> struct Dft<16, SIGN> { static RC_HD void run(float2* v) { dft_composite<4, 4, SIGN>(v); } };
+template <int SIGN> struct Dft<25, SIGN> { static RC_HD void run(float2* v) { dft_composite<5, 5, SIGN>(v); } };
+
+// --------------------------------------------------------------- pass record
+constexpr int kMaxStages = 16;
+constexpr int kMaxPasses = 4;
+constexpr int kSmemBudgetElems = 25600;      // float2 elements per CTA (200 KiB)
+
+struct FftPass {
+    int R;                 // transform length handled in shared memory
+    int T, logT;           // columns per CTA tile (power of two)
+    int nstage;
+    int radix[kMaxStages]; // product = R, DIT order (stage 0 has no twiddles)
+    long long n;           // full transform length
+    long long Ns;          // product of the R's of earlier passes
+    long long stride;      // n / R : input row stride == number of columns
+    unsigned long long M;  // Ns * R : modulus of the inter-pass twiddle
+    int tw_shift;          // W_M^q = lo[q & mask] * hi[q >> shift]
+    unsigned tw_mask;
+    const double2* tw_lo;
+    const double2* tw_hi;
+    const float2* twR;     // W_R^m forward, m in [0, R)
+    const int* pos;        // time index t -> shared-memory slot (digit reversal)
+    int threads;
+    int smem_elems;
+};
+
+RC_HD int fft_phys(const FftPass& P, int p, int c) {
+    return P.T > 1 ? p * (P.T + 1) + c : p + (p >> 4);
+}
+
+RC_HD double2 fft_tw64(const FftPass& P, unsigned long long q) {
+    if (q >= P.M) q %= P.M;
+    double2 a = ldg(P.tw_lo + (unsigned)(q & P.tw_mask));
+    double2 b = ldg(P.tw_hi + (unsigned)(q >> P.tw_shift));
+    return cmul64(a, b);
+}
+
+// ------------------------------------------------------------ generic I/O ops
+struct LoadC64 {          // contiguous complex64 batches
+    const float2* p;
+    long long batch_stride;
+    RC_HD float2 operator()(int b, long long i) const { return ldg(p + b * batch_stride + i); }
+};
+struct StoreC64 {
+    float2* p;
+    long long batch_stride;
+    float scale;
+    RC_HD void operator()(int b, long long i, float2 v) const {
+        p[b * batch_stride + i] = make_float2(v.x * scale, v.y * scale);
+    }
+};
+
+// ------------------------------------------------------------- pass phases
+template <class LoadOp, int SIGN>
+RC_HD void fft_pass_load(float2* sm, const FftPass& P, const LoadOp& ld, int batch,
+                         long long j0, int tid, int nthreads) {
+    const int c = tid & (P.T - 1);
+    const int t0 = tid >> P.logT;
+    const int dt = nthreads >> P.logT;
+    const long long j = j0 + c;
+    const bool active = j < P.stride;
+    const bool use_tw = P.Ns > 1;
+    double2 w = make_double2(1.0, 0.0), ws = w;
+    if (use_tw && active) {
+        unsigned long long k = (unsigned long long)(j % P.Ns);
+        w = fft_tw64(P, (unsigned long long)t0 * k);
+        ws = fft_tw64(P, (unsigned long long)dt * k);
+    }
+    for (int t = t0; t < P.R; t += dt) {
+        float2 v = make_float2(0.f, 0.f);
+        if (active) {
+            v = ld(batch, j + (long long)t * P.stride);
+            if (use_tw) {
+                v = cmul(v, make_float2((float)w.x, (float)(SIGN < 0 ? w.y : -w.y)));
+                w = cmul64(w, ws);
+            }
+        }
+        sm[fft_phys(P, ldg(P.pos + t), c)] = v;
+    }
+}
+
+template <int R, int SIGN>
+RC_HD void fft_stage_item(float2* sm, const FftPass& P, int Lprev, int item) {
+    const int c = item & (P.T - 1);
+    const int bf = item >> P.logT;
+    const int blk = bf / Lprev;
+    const int u = bf - blk * Lprev;
+    const int base = blk * (Lprev * R) + u;
+    const int twstep = (P.R / (Lprev * R)) * u;   // W_{L_s}^{u} expressed on the W_R table
+    float2 v[R];
+#pragma unroll
+    for (int m = 0; m < R; m++) v[m] = sm[fft_phys(P, base + m * Lprev, c)];
+    if (u > 0) {
+#pragma unroll
+        for (int m = 1; m < R; m++) {
+            float2 w = ldg(P.twR + twstep * m);
+            if (SIGN > 0) w.y = -w.y;
+            v[m] = cmul(v[m], w);
+        }
+    }
+    Dft<R, SIGN>::run(v);
+#pragma unroll
+    for (int k = 0; k < R; k++) sm[fft_phys(P, base + k * Lprev, c)] = v[k];
+}
+
+template <int R, int SIGN>
+RC_HD void fft_stage(float2* sm, const FftPass& P, int Lprev, int tid, int nthreads) {
+    const int nitems = (P.R / R) << P.logT;
+    for (int item = tid; item < nitems; item += nthreads) fft_stage_item<R, SIGN>(sm, P, Lprev, item);
+}
+
+template <int SIGN>
+RC_HD void fft_stage_dispatch(float2* sm, const FftPass& P, int radix, int Lprev, int tid, int nthreads) {
+    switch (radix) {
+        case 2: fft_stage<2, SIGN>(sm, P, Lprev, tid, nthreads); break;
+        case 3: fft_stage<3, SIGN>(sm, P, Lprev, tid, nthreads); break;
+        case 4: fft_stage<4, SIGN>(sm, P, Lprev, tid, nthreads); break;
+        case 5: fft_stage<5, SIGN>(sm, P, Lprev, tid, nthreads); break;
+        case 8: fft_stage<8, SIGN>(sm, P, Lprev, tid, nthreads); break;
+        case 10: fft_stage<10, SIGN>(sm, P, Lprev, tid, nthreads); break;
+        case 16: fft_stage<16, SIGN>(sm, P, Lprev, tid, nthreads); break;
+        case 25: fft_stage<25, SIGN>(sm, P, Lprev, tid, nthreads); break;
+        default: break;
+    }
+}
+
+template <class StoreOp>
+RC_HD void fft_pass_store(const float2* sm, const FftPass& P, const StoreOp& st, int batch,
+                          long long j0, int tid, int nthreads) {
+    if (P.Ns == 1) {
+        // First pass: the tile's output is the contiguous run [j0*R, (j0+T)*R), K fastest.
+        for (int c = 0; c < P.T; c++) {
+            const long long j = j0 + c;
+            if (j >= P.stride) break;
+            for (int K = tid; K < P.R; K += nthreads) st(batch, j * P.R + K, sm[fft_phys(P, K, c)]);
+        }
+    } else {
+        const int c = tid & (P.T - 1);
+        const long long j = j0 + c;
+        if (j >= P.stride) return;
+        const long long q = j / P.Ns;
+        const long long base = q * P.Ns * P.R + (j - q * P.Ns);
+        for (int K = tid >> P.logT; K < P.R; K += nthreads >> P.logT)
+            st(batch, base + (long long)K * P.Ns, sm[fft_phys(P, K, c)]);
+    }
+}
+
+#if defined(__CUDACC__) && !defined(RC_EMULATE)
+template <class LoadOp, class StoreOp, int SIGN>
+__global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass P, const LoadOp ld, const StoreOp st) {
+    extern __shared__ float2 rc_fft_smem[];
+    float2* sm = rc_fft_smem;
+    const int batch = blockIdx.y + blockIdx.z * gridDim.y;
+    const long long j0 = (long long)blockIdx.x * P.T;
+    fft_pass_load<LoadOp, SIGN>(sm, P, ld, batch, j0, threadIdx.x, blockDim.x);
+    __syncthreads();
+    int Lprev = 1;
+    for (int s = 0; s < P.nstage; s++) {
+        fft_stage_dispatch<SIGN>(sm, P, P.radix[s], Lprev, threadIdx.x, blockDim.x);
+        __syncthreads();
+        Lprev *= P.radix[s];
+    }
+    fft_pass_store<StoreOp>(sm, P, st, batch, j0, threadIdx.x, blockDim.x);
+}
+#endif
+
+// ------------------------------------------------------------------- planning
+struct FftPlan {
+    long long n = 0;
+    int npass = 0;
+    FftPass pass[kMaxPasses];
+};
+
+// Memory source for the plan tables: device (product) or host (CPU emulation).
+struct TableStore {
+    bool on_device;
+    std::vector<void*> owned;
+    std::map<std::string, const void*> cache;
+    explicit TableStore(bool dev) : on_device(dev) {}
+    ~TableStore() { release(); }
+    void release() {
+        for (void* p : owned) {
+            if (on_device) cudaFree(p); else free(p);
+        }
+        owned.clear();
+        cache.clear();
+    }
+    const void* put(const std::string& key, const void* host, size_t bytes, cudaError_t* err) {
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+        void* p = nullptr;
+        if (on_device) {
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e == cudaSuccess) e = cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { if (err) *err = e; return nullptr; }
+        } else {
+            p = malloc(bytes);
+            memcpy(p, host, bytes);
+        }
+        owned.push_back(p);
+        cache[key] = p;
+        return p;
+    }
+    bool has(const std::string& key) const { return cache.count(key) != 0; }
+};
+
+inline bool fft_size_supported(long long n) {
+    if (n < 1) return false;
+    for (int p : {2, 3, 5}) while (n % p == 0) n /= p;
+    return n == 1;
+}
+
+// Radix schedule for one in-shared-memory transform of length R.
+inline std::vector<int> fft_radix_schedule(int R) {
+    int e2 = 0, e3 = 0, e5 = 0;
+    while (R % 2 == 0) { R /= 2; e2++; }
+    while (R % 3 == 0) { R /= 3; e3++; }
+    while (R % 5 == 0) { R /= 5; e5++; }
+    std::vector<int> r;
+    while (e5 >= 2) { r.push_back(25); e5 -= 2; }
+    if (e5 == 1) { if (e2 >= 1) { r.push_back(10); e2--; } else r.push_back(5); }
+    while (e2 >= 4) { r.push_back(16); e2 -= 4; }
+    if (e2 == 3) r.push_back(8);
+    else if (e2 == 2) r.push_back(4);
+    else if (e2 == 1) r.push_back(2);
+    while (e3 > 0) { r.push_back(3); e3--; }
+    if (r.empty()) r.push_back(1);
+    return r;
+}
+
+inline int fft_max_R(int T) { return T > 1 ? kSmemBudgetElems / (T + 1) : (kSmemBudgetElems * 16) / 17 - 1; }
+
+// Split n into the fewest pass lengths that fit shared memory; balanced factors.
+inline bool fft_choose_passes(long long n, std::vector<int>& Rs, int& T) {
+    Rs.clear();
+    if (n <= fft_max_R(1)) { Rs.push_back((int)n); T = 1; return true; }
+    std::vector<long long> divs;
+    for (long long d = 1; d * d <= n; d++)
+        if (n % d == 0) { divs.push_back(d); if (d != n / d) divs.push_back(n / d); }
+    for (int Tc : {16, 8}) {
+        const long long lim = fft_max_R(Tc);
+        // two passes
+        long long best = 0;
+        for (long long d : divs) {
+            long long e = n / d;
+            if (d <= lim && e <= lim && d >= e) { if (best == 0 || d < best) best = d; }
+        }
+        if (best) { Rs = {(int)best, (int)(n / best)}; T = Tc; return true; }
+    }
+    for (int Tc : {16, 8}) {
+        const long long lim = fft_max_R(Tc);
+        long long bestmax = 0; long long ba = 0, bb = 0, bc = 0;
+        for (long long a : divs) {
+            if (a > lim) continue;
+            long long rest = n / a;
+            for (long long b : divs) {
+                if (b > a || b > lim || rest % b) continue;
+                long long c = rest / b;
+                if (c > b || c > lim) continue;
+                if (bestmax == 0 || a < bestmax) { bestmax = a; ba = a; bb = b; bc = c; }
+            }
+        }
+        if (bestmax) { Rs = {(int)ba, (int)bb, (int)bc}; T = Tc; return true; }
+    }
+    return false;
+}
+
+inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store) {
+    if (!fft_size_supported(n)) return cudaErrorInvalidValue;
+    std::vector<int> Rs;
+    int T = 1;
+    if (!fft_choose_passes(n, Rs, T)) return cudaErrorInvalidValue;
+    plan.n = n;
+    plan.npass = (int)Rs.size();
+    long long Ns = 1;
+    cudaError_t err = cudaSuccess;
+    for (int i = 0; i < plan.npass; i++) {
+        FftPass& P = plan.pass[i];
+        memset(&P, 0, sizeof(P));
+        P.R = Rs[i];
+        P.T = T;
+        P.logT = 0;
+        while ((1 << P.logT) < T) P.logT++;
+        std::vector<int> rad = fft_radix_schedule(P.R);
+        if (rad.size() == 1 && rad[0] == 1) rad.clear();
+        P.nstage = (int)rad.size();
+        for (int s = 0; s < P.nstage; s++) P.radix[s] = rad[s];
+        P.n = n;
+        P.Ns = Ns;
+        P.stride = n / P.R;
+        P.M = (unsigned long long)Ns * P.R;
+        // W_R table (forward)
+        {
+            std::string key = "twR:" + std::to_string(P.R);
+            if (!store.has(key)) {
+                std::vector<float2> t(P.R);
+                for (int m = 0; m < P.R; m++) {
+                    long double a = -2.0L * 3.14159265358979323846264338327950288L * m / P.R;
+                    t[m] = make_float2((float)cosl(a), (float)sinl(a));
+                }
+                store.put(key, t.data(), t.size() * sizeof(float2), &err);
+            }
+            P.twR = (const float2*)store.put(key, nullptr, 0, &err);
+        }
+        // digit-reversal table
+        {
+            std::string key = "pos:" + std::to_string(P.R);
+            if (!store.has(key)) {
+                std::vector<int> pos(P.R);
+                for (int t = 0; t < P.R; t++) {
+                    int tmp = t, p = 0;
+                    std::vector<int> L(P.nstage + 1, 1);
+                    for (int s = 0; s < P.nstage; s++) L[s + 1] = L[s] * P.radix[s];
+                    for (int s = P.nstage - 1; s >= 0; s--) {
+                        int m = tmp % P.radix[s];
+                        tmp /= P.radix[s];
+                        p += m * L[s];
+                    }
+                    pos[t] = p;
+                }
+                store.put(key, pos.data(), pos.size() * sizeof(int), &err);
+            }
+            P.pos = (const int*)store.put(key, nullptr, 0, &err);
+        }
+        // inter-pass twiddle tables W_M, M = Ns*R (fp64, forward)
+        if (Ns > 1) {
+            int bits = 0;
+            while ((1ULL << bits) < P.M) bits++;
+            P.tw_shift = (bits + 1) / 2;
+            P.tw_mask = (1u << P.tw_shift) - 1u;
+            std::string key = "twM:" + std::to_string(P.M);
+            if (!store.has(key + ":lo")) {
+                size_t nlo = (size_t)1 << P.tw_shift;
+                size_t nhi = (size_t)((P.M >> P.tw_shift) + 1);
+                std::vector<double2> lo(nlo), hi(nhi);
+                const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+                for (size_t q = 0; q < nlo; q++) {
+                    long double a = -tau * (long double)q / (long double)P.M;
+                    lo[q] = make_double2((double)cosl(a), (double)sinl(a));
+                }
+                for (size_t q = 0; q < nhi; q++) {
+                    unsigned long long qq = ((unsigned long long)q << P.tw_shift) % P.M;
+                    long double a = -tau * (long double)qq / (long double)P.M;
+                    hi[q] = make_double2((double)cosl(a), (double)sinl(a));
+                }
+                store.put(key + ":lo", lo.data(), nlo * sizeof(double2), &err);
+                store.put(key + ":hi", hi.data(), nhi * sizeof(double2), &err);
+            }
+            P.tw_lo = (const double2*)store.put(key + ":lo", nullptr, 0, &err);
+            P.tw_hi = (const double2*)store.put(key + ":hi", nullptr, 0, &err);
+        }
+        P.smem_elems = T > 1 ? P.R * (T + 1) : P.R + (P.R >> 4) + 1;
+        long long work = (long long)P.R * T;
+        int th = (int)((work / 8 + 31) / 32 * 32);
+        if (th < 64) th = 64;
+        if (th > 512) th = 512;
+        P.threads = th;
+        if (err != cudaSuccess) return err;
+        Ns *= P.R;
+    }
+    return cudaSuccess;
+}
+
+#if defined(__CUDACC__) && !defined(RC_EMULATE)
+// Run all passes.  work0/work1: scratch of batch*n float2 each (needed when
+// npass >= 2 / npass == 3).  LoadOp feeds pass 0, StoreOp drains the last pass.
+template <int SIGN, class LoadOp, class StoreOp>
+cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const StoreOp& st,
+                     float2* work0, float2* work1, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    for (int i = 0; i < plan.npass; i++) {
+        const FftPass& P = plan.pass[i];
+        long long tiles = (P.stride + P.T - 1) / P.T;
+        int by = batch, bz = 1;
+        while (by > 65535) { bz *= 2; by = (batch + bz - 1) / bz; }
+        if ((long long)by * bz != batch) return cudaErrorInvalidValue;   // caller keeps batch <= 65535 or even
+        dim3 grid((unsigned)tiles, (unsigned)by, (unsigned)bz);
+        size_t smem = (size_t)P.smem_elems * sizeof(float2);
+        const bool first = i == 0, last = i == plan.npass - 1;
+        float2* src = (i == 1) ? work0 : work1;
+        float2* dst = (i == 0) ? work0 : work1;
+        LoadC64 lmid{src, plan.n};
+        StoreC64 smid{dst, plan.n, 1.0f};
+        cudaError_t e;
+#define RC_LAUNCH(LD, ST, ldv, stv)                                                                   \
+        e = cudaFuncSetAttribute(fft_pass_kernel<LD, ST, SIGN>,                                       \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+        if (e != cudaSuccess) return e;                                                               \
+        fft_pass_kernel<LD, ST, SIGN><<<grid, P.threads, smem, stream>>>(P, ldv, stv);
+        if (first && last) { RC_LAUNCH(LoadOp, StoreOp, ld, st) }
+        else if (first)    { RC_LAUNCH(LoadOp, StoreC64, ld, smid) }
+        else if (last)     { RC_LAUNCH(LoadC64, StoreOp, lmid, st) }
+        else               { RC_LAUNCH(LoadC64, StoreC64, lmid, smid) }
+#undef RC_LAUNCH
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+#endif
+
+}  // namespace rc

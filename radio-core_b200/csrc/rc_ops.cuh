@@ -1,0 +1,457 @@
+// rc_ops.cuh -- the per-stage arithmetic of the receive chain as load/store
+// functors fused into the FFT passes and as elementwise functors.
+//
+// Each functor restates one step of the reference (file:line given) in fp32
+// (fp64 where a short accumulation makes it free).  All are __host__ __device__
+// so tests/native can replay them on the CPU.
+#pragma once
+
+#include "rc_backend.cuh"
+
+namespace rc {
+
+constexpr float kInvPiF = 0.31830988618379067154f;
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+// Periodic cosine window after fftshift, evaluated at bin k of an n-bin
+// spectrum:  W(k) = a0 + a1*cos(2*pi*k/n + phi), phi = 0 (n even) or pi/n (odd).
+// (tuner.py:155-157 'hann' -> a0=a1=0.5; decimate.py:32-33 'hamm' -> .54/.46)
+struct ShiftedWindow {
+    float a0, a1;
+    double two_over_n;    // 2/n
+    float phi_over_pi;    // phi/pi
+    RC_HD float at_centered(long long kc) const {   // kc in (-n/2, n/2]
+        float th = (float)((double)kc * two_over_n) + phi_over_pi;
+#ifdef __CUDA_ARCH__
+        return a0 + a1 * cospif(th);
+#else
+        return a0 + a1 * (float)cos(kPi * (double)th);
+#endif
+    }
+};
+
+inline ShiftedWindow make_window(bool hann, long long n) {
+    ShiftedWindow w;
+    w.a0 = hann ? 0.5f : 0.54f;
+    w.a1 = hann ? 0.5f : 0.46f;
+    w.two_over_n = 2.0 / (double)n;
+    w.phi_over_pi = (n % 2 == 0) ? 0.0f : (float)(1.0 / (double)n);
+    return w;
+}
+
+// ---------------------------------------------------------------------------
+// LoadOp: two-sided Fourier resampling in the frequency domain.
+// Restates scipy.signal.resample's two-sided branch as called by
+// Tuner.run (tuner.py:159-161: roll, Hann, domain='freq') and by Decimate.run
+// on complex input (decimate.py:48: Hamming, no roll): logical bin j of the
+// num-point inverse FFT, gathered from the n_x-point spectrum X.
+// ---------------------------------------------------------------------------
+struct LoadResampleGather {
+    const float2* X;           // spectrum, n_x bins
+    long long x_batch_stride;  // 0 when every batch entry reads the same spectrum (Tuner)
+    const long long* roll;     // per-batch roll in bins (may be null -> 0)
+    long long n_x, num, m, m2;
+    ShiftedWindow win;
+    float scale;               // num / n_x
+
+    RC_HD float2 src(int b, long long k, long long r) const {   // X[(k-r) mod n_x] * W(k)
+        long long s = k - r;
+        if (s < 0) s += n_x; else if (s >= n_x) s -= n_x;
+        const long long kc = (2 * k > n_x) ? k - n_x : k;
+        const float w = win.at_centered(kc) * scale;
+        float2 v = ldg(X + b * x_batch_stride + s);
+        return make_float2(v.x * w, v.y * w);
+    }
+    RC_HD float2 operator()(int b, long long j) const {
+        const long long r = roll ? ldg(roll + b) : 0;
+        float2 v = make_float2(0.f, 0.f);
+        if (j < m2) v = src(b, j, r);
+        else if (j >= num - (m - m2)) v = src(b, n_x - (num - j), r);
+        if ((m & 1) == 0) {
+            if (num < n_x) {
+                if (j == num - m / 2) v = cadd(v, src(b, n_x - m / 2, r));
+            } else if (n_x < num) {
+                if (j == m / 2) v = cscale(v, 0.5f);
+                else if (j == num - m / 2) v = cscale(src(b, m / 2, r), 0.5f);
+            }
+        }
+        return v;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// LoadOp: FM discriminator feeding a packed real FFT.
+// fm.py:60-65: angle -> unwrap -> diff -> pad(1,0) -> /pi, i.e.
+// d[0] = 0, d[n] = wrap(angle(y[n]) - angle(y[n-1]))/pi = angle(y[n]*conj(y[n-1]))/pi.
+// Element i of the half-length complex sequence is (d[2i], d[2i+1]).
+// ---------------------------------------------------------------------------
+RC_HD float fm_step(float2 cur, float2 prev) {
+    const float re = cur.x * prev.x + cur.y * prev.y;
+    const float im = cur.y * prev.x - cur.x * prev.y;
+    return atan2f(im, re) * kInvPiF;
+}
+
+struct LoadDiscriminatorPacked {
+    const float2* y;
+    long long batch_stride;
+    RC_HD float2 operator()(int b, long long i) const {
+        const float2* p = y + b * batch_stride + 2 * i;
+        const float2 y0 = ldg(p), y1 = ldg(p + 1);
+        const float d0 = (i == 0) ? 0.f : fm_step(y0, ldg(p - 1));
+        return make_float2(d0, fm_step(y1, y0));
+    }
+};
+
+// Elementwise variant (used for odd sizes and by tests): d[b][n].
+struct DiscriminatorEw {
+    const float2* y;
+    float* d;
+    long long n;
+    RC_HD void operator()(int b, long long i) const {
+        const float2* p = y + b * n + i;
+        d[b * n + i] = (i == 0) ? 0.f : fm_step(ldg(p), ldg(p - 1));
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Real-FFT algebra on a half-length complex FFT.
+// Z = FFT_h(z), z[i] = x[2i] + i x[2i+1], n = 2h.  rfft bin k (0 <= k <= h):
+//   X[k] = E + W_n^k * O,  E = (Z[k] + conj Z[h-k])/2,  O = -i (Z[k] - conj Z[h-k])/2
+// rtw[k] = W_n^k = exp(-2 pi i k / n).
+// ---------------------------------------------------------------------------
+RC_HD float2 rfft_bin(const float2* Z, long long h, long long k, const float2* rtw) {
+    const float2 zk = ldg(Z + (k == h ? 0 : k));
+    const float2 zm = cconj(ldg(Z + (k == 0 ? 0 : h - k)));
+    const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
+    const float2 dlt = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
+    const float2 o = make_float2(dlt.y, -dlt.x);   // -i * dlt
+    return cadd(e, cmul(ldg(rtw + k), o));
+}
+
+// Inverse: half-spectrum Y[0..h'] of a real signal of length num = 2h'  ->
+// Z'[k] = E + i*O with E = (Y[k] + conj Y[h'-k])/2, O = (Y[k] - conj Y[h'-k])/2 * W_num^{-k};
+// z = IFFT_h'(Z')/h' gives z[i] = x[2i] + i x[2i+1].   itw[k] = exp(+2 pi i k / num).
+RC_HD float2 irfft_pack(float2 ya, float2 yb_conj, float2 itw_k) {
+    const float2 e = make_float2(0.5f * (ya.x + yb_conj.x), 0.5f * (ya.y + yb_conj.y));
+    const float2 dlt = make_float2(0.5f * (ya.x - yb_conj.x), 0.5f * (ya.y - yb_conj.y));
+    const float2 o = cmul(dlt, itw_k);
+    return make_float2(e.x - o.y, e.y + o.x);      // E + i*O
+}
+
+// Parameters of scipy.signal.resample's rfft branch (decimate.py:48 on real
+// input): fold window Wf[k] = a0 + a1*cos(phi)*cos(2 pi k/n), keep m2 bins,
+// double/halve the unpaired bin m/2, scale by num/n_x.
+struct RealResampleSpec {
+    long long n_x, num, h, hp, m, m2;   // h = n_x/2, hp = num/2
+    float a0, a1c;                      // a1c = a1*cos(phi)
+    float scale;                        // (num/n_x) * (1/hp)  (inverse-FFT normalisation folded in)
+    float nyq;                          // factor on bin m/2 (2, 0.5 or 1)
+    const float2* rtw;                  // W_{n_x}^k, k in [0, min(m2, h+1))
+    const float2* itw;                  // W_{num}^{-k}, k in [0, hp)
+
+    // windowed, scaled rfft bin k of the resampled spectrum (0 beyond m2)
+    RC_HD float2 bin(const float2* Z, long long k, int taper_pow) const {
+        if (k >= m2) return make_float2(0.f, 0.f);
+        float2 x = rfft_bin(Z, h, k, rtw);
+        float w = a0 + a1c * ldg(rtw + k).x;
+        if (taper_pow == 2) w *= w;
+        w *= scale;
+        if ((m & 1) == 0 && k == m / 2) w *= nyq;
+        x = make_float2(x.x * w, x.y * w);
+        if (k == 0 || k == hp) x.y = 0.f;      // c2r ignores Im of DC / Nyquist
+        return x;
+    }
+};
+
+// Elementwise: Z (FFT of packed real input, per batch h bins) -> Z' (input of the
+// packed inverse FFT, per batch hp bins).  One kernel = rfft post-processing +
+// window + truncation + irfft pre-processing.
+struct SpecResampleEw {
+    RealResampleSpec s;
+    const float2* Z;      // [batch][h]
+    float2* Zp;           // [batch][hp]
+    RC_HD void operator()(int b, long long k) const {
+        const float2* z = Z + b * s.h;
+        const float2 ya = s.bin(z, k, 1);
+        const float2 yb = cconj(s.bin(z, s.hp - k, 1));
+        Zp[b * s.hp + k] = irfft_pack(ya, yb, ldg(s.itw + k));
+    }
+};
+
+// WBFM audio spectra (wbfm.py:86-87 with linearity of Decimate):
+// L = D(mpx)+D(lmr), R = D(mpx)-D(lmr);  rfft(mpx)[k] = X_d[k]*Wf[k]  (the
+// same-size FM(B,B) resample, wbfm.py:42-43), so D(mpx) carries Wf twice.
+struct SpecStereoEw {
+    RealResampleSpec s;
+    const float2* Zd;     // [batch][h]  FFT of packed discriminator
+    const float2* Zl;     // [batch][h]  FFT of packed lmr
+    float2* Zp;           // [batch][2][hp]  (L then R)
+    RC_HD void operator()(int b, long long k) const {
+        const float2* zd = Zd + b * s.h;
+        const float2* zl = Zl + b * s.h;
+        const long long kb = s.hp - k;
+        const float2 ma = s.bin(zd, k, 2), la = s.bin(zl, k, 1);
+        const float2 mb = cconj(s.bin(zd, kb, 2)), lb = cconj(s.bin(zl, kb, 1));
+        const float2 tw = ldg(s.itw + k);
+        Zp[(b * 2 + 0) * s.hp + k] = irfft_pack(cadd(ma, la), cadd(mb, lb), tw);
+        Zp[(b * 2 + 1) * s.hp + k] = irfft_pack(csub(ma, la), csub(mb, lb), tw);
+    }
+};
+
+// Hilbert transform spectrum (pll.py:34): analytic z = p + i*hhat with
+// Hhat[k] = -i P[k] (0 < k < n/2), 0 at DC and Nyquist.  Output packed for the
+// half-length inverse FFT; s.scale must be 1/h, s.m2 = h+1, window a0=1,a1c=0.
+struct SpecHilbertEw {
+    RealResampleSpec s;
+    const float2* Z;
+    float2* Zp;
+    RC_HD float2 hbin(const float2* z, long long k) const {
+        if (k == 0 || k == s.h) return make_float2(0.f, 0.f);
+        const float2 p = rfft_bin(z, s.h, k, s.rtw);
+        return make_float2(p.y * s.scale, -p.x * s.scale);     // -i * P
+    }
+    RC_HD void operator()(int b, long long k) const {
+        const float2* z = Z + b * s.h;
+        Zp[b * s.h + k] = irfft_pack(hbin(z, k), cconj(hbin(z, s.h - k)), ldg(s.itw + k));
+    }
+};
+
+// StoreOp of the Hilbert inverse FFT: element i carries (hhat[2i], hhat[2i+1]).
+// pll.py:57-58 image(2) = Im(z^2)/|z^2| = 2 p hhat / (p^2 + hhat^2);
+// wbfm.py:83 lmr = image(2) * mpx * 1.0175.
+struct StoreLmrPacked {
+    const float* pilot;   // [batch][n]
+    const float* mpx;     // [batch][n]
+    float* lmr;           // [batch][n]
+    long long n;
+    RC_HD static float one(float p, float hh, float m) {
+        const float s2 = (2.0f * p * hh) / (p * p + hh * hh);
+        return s2 * m * 1.0175f;
+    }
+    RC_HD void operator()(int b, long long i, float2 v) const {
+        const long long o = b * n + 2 * i;
+        const float2 p = *(const float2*)(pilot + o);
+        const float2 m = *(const float2*)(mpx + o);
+        *(float2*)(lmr + o) = make_float2(one(p.x, v.x, m.x), one(p.y, v.y, m.y));
+    }
+};
+
+// StoreOp: analytic signal z[n] = p[n] + i*hhat[n] (PLL.step standalone).
+struct StoreAnalyticPacked {
+    const float* sig;
+    float2* z;
+    long long n;
+    RC_HD void operator()(int b, long long i, float2 v) const {
+        const long long o = b * n + 2 * i;
+        z[o] = make_float2(sig[o], v.x);
+        z[o + 1] = make_float2(sig[o + 1], v.y);
+    }
+};
+
+// PLL.real / PLL.image (pll.py:36-58): Re or Im of z^mult / |z^mult|.
+struct PllEvalEw {
+    const float2* z;
+    float* out;
+    long long n;
+    float mult;
+    int imag;
+    RC_HD void operator()(int b, long long i) const {
+        const float2 v = z[b * n + i];
+        float r;
+        if (mult == 2.0f) {
+            const float d = v.x * v.x + v.y * v.y;
+            r = imag ? (2.0f * v.x * v.y) / d : (v.x * v.x - v.y * v.y) / d;
+        } else {
+            const float a = mult * atan2f(v.y, v.x);
+            r = (v.x == 0.f && v.y == 0.f) ? nanf("") : (imag ? sinf(a) : cosf(a));
+        }
+        out[b * n + i] = r;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Odd-length fallback of the real resampler (decimate.py:48 on real input when
+// a size is odd): full-length complex FFT of (x, 0), Hermitian re-expansion of
+// the kept bins, full-length inverse FFT, real part.
+// ---------------------------------------------------------------------------
+struct LoadRealAsComplex {
+    const float* x;
+    long long batch_stride;
+    RC_HD float2 operator()(int b, long long i) const { return make_float2(ldg(x + b * batch_stride + i), 0.f); }
+};
+
+struct LoadHermitianResample {
+    const float2* X;          // [batch][n_x] full spectrum of the real input
+    long long n_x, num, m, m2;
+    float a0, a1c;            // folded window a0 + a1c*cos(2 pi k / n_x)
+    double two_over_n;
+    float scale, nyq;
+    RC_HD float2 operator()(int b, long long j) const {
+        const bool neg = 2 * j > num;
+        const long long k = neg ? num - j : j;
+        if (k >= m2) return make_float2(0.f, 0.f);
+        float2 v = ldg(X + b * n_x + k);
+        const float th = (float)((double)k * two_over_n);
+#ifdef __CUDA_ARCH__
+        float w = a0 + a1c * cospif(th);
+#else
+        float w = a0 + a1c * (float)cos(kPi * (double)th);
+#endif
+        w *= scale;
+        if ((m & 1) == 0 && k == m / 2) w *= nyq;
+        v = make_float2(v.x * w, v.y * w);
+        if (k == 0 || 2 * k == num) v.y = 0.f;       // c2r ignores Im of DC / Nyquist
+        if (neg) v.y = -v.y;
+        return v;
+    }
+};
+
+struct StoreRealPart {
+    float* out;
+    long long batch_stride;
+    RC_HD void operator()(int b, long long i, float2 v) const { out[b * batch_stride + i] = v.x; }
+};
+
+// ---------------------------------------------------------------------------
+// Zero-phase FIR (bandpass.py:72 filtfilt(b, 1, x), padtype 'odd').
+// With an FIR the lfilter_zi start-up terms only touch the first len(b)-1
+// samples of the 3*len(b) extension, which filtfilt crops, so the result is
+// exactly  out[n] = sum_j g[j] * xe[n + j - K],  g = b (*) reversed(b),
+// K = len(b)-1, xe = x extended by odd reflection about both end samples.
+// ---------------------------------------------------------------------------
+struct FiltFiltEw {
+    const float* x;
+    float* out;
+    const double* g;     // 2K+1 autocorrelation taps
+    long long n;
+    int K;
+    RC_HD double xe(const float* xb, long long i) const {
+        if (i < 0) return 2.0 * (double)xb[0] - (double)xb[-i];
+        if (i >= n) return 2.0 * (double)xb[n - 1] - (double)xb[2 * (n - 1) - i];
+        return (double)xb[i];
+    }
+    RC_HD void operator()(int b, long long i) const {
+        const float* xb = x + b * n;
+        double acc = 0.0;
+        if (i >= K && i + K < n) {
+            for (int j = 0; j <= 2 * K; j++) acc += g[j] * (double)xb[i + j - K];
+        } else {
+            for (int j = 0; j <= 2 * K; j++) acc += g[j] * xe(xb, i + j - K);
+        }
+        out[b * n + i] = (float)acc;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Audio epilogue: stateful FIR de-emphasis (deemphasis.py:64 lfilter with
+// carried zi), block mean removal and clip (mfm.py:64-65, wbfm.py:97-100).
+// Phase functions are per-thread; the CTA owns one channel (nch audio channels).
+// ---------------------------------------------------------------------------
+struct EpilogueParams {
+    const float* in;      // [batch][nch][A]   resampled audio
+    float* out;           // [batch][A][nch]   interleaved, final
+    double* zi;           // [batch][nch][K]   carried filter state (K = ntaps-1)
+    double* zi_next;      // scratch of the same shape
+    const float* taps;    // ntaps FIR taps (float32 values, as the reference stores them)
+    long long A;
+    int nch, ntaps;
+    int deemph;           // 0: no filter (plain FM)
+    int dc_clip;          // 1: subtract block mean and clip to +-0.999
+};
+
+RC_HD double epi_fir(const EpilogueParams& p, int b, int ch, long long n) {
+    const float* a = p.in + ((long long)b * p.nch + ch) * p.A;
+    if (!p.deemph) return (double)a[n];
+    const int K = p.ntaps - 1;
+    double acc = 0.0;
+    const int kmax = (n < K) ? (int)n : K;
+    for (int k = 0; k <= kmax; k++) acc += (double)ldg(p.taps + k) * (double)a[n - k];
+    if (n < K) acc += p.zi[((long long)b * p.nch + ch) * K + n];
+    return acc;
+}
+
+// zf[i] = sum_{k>i} b[k] a[A-(k-i)]  (+ zi[i+A] when the block is shorter than the filter)
+RC_HD double epi_next_state(const EpilogueParams& p, int b, int ch, int i) {
+    const float* a = p.in + ((long long)b * p.nch + ch) * p.A;
+    const int K = p.ntaps - 1;
+    double acc = 0.0;
+    for (int k = i + 1; k <= K; k++) {
+        const long long idx = p.A - (k - i);
+        if (idx >= 0) acc += (double)ldg(p.taps + k) * (double)a[idx];
+    }
+    if (i + p.A < K) acc += p.zi[((long long)b * p.nch + ch) * K + i + p.A];
+    return acc;
+}
+
+RC_HD float epi_finish(const EpilogueParams& p, double v, double mean) {
+    if (!p.dc_clip) return (float)v;
+    v -= mean;
+    v = v < -0.999 ? -0.999 : (v > 0.999 ? 0.999 : v);
+    return (float)v;
+}
+
+#if defined(__CUDACC__) && !defined(RC_EMULATE)
+constexpr int kEpiThreads = 1024;
+__global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpilogueParams p) {
+    __shared__ double red[kEpiThreads];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const long long total = p.A * p.nch;
+    double sum = 0.0;
+    for (long long e = tid; e < total; e += kEpiThreads) {
+        const int ch = (int)(e % p.nch);
+        const long long n = e / p.nch;
+        const double v = epi_fir(p, b, ch, n);
+        sum += v;
+        p.out[(long long)b * total + e] = (float)v;      // staged; finished below by the same thread
+    }
+    red[tid] = sum;
+    __syncthreads();
+    for (int s = kEpiThreads / 2; s > 0; s >>= 1) {
+        if (tid < s) red[tid] += red[tid + s];
+        __syncthreads();
+    }
+    const double mean = red[0] / (double)total;
+    if (p.deemph) {
+        const int K = p.ntaps - 1;
+        for (int e = tid; e < K * p.nch; e += kEpiThreads)
+            p.zi_next[(long long)b * p.nch * K + e] = epi_next_state(p, b, e / K, e % K);
+    }
+    if (p.dc_clip) {
+        for (long long e = tid; e < total; e += kEpiThreads) {
+            // re-evaluate in fp64 rather than re-reading the fp32 staging value
+            const double v = epi_fir(p, b, (int)(e % p.nch), e / p.nch);
+            p.out[(long long)b * total + e] = epi_finish(p, v, mean);
+        }
+    }
+}
+#endif
+
+inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStream_t stream) {
+#ifdef RC_EMULATE
+    const int nth = 1024;
+    const long long total = p.A * p.nch;
+    for (int b = 0; b < batch; b++) {
+        std::vector<double> red(nth, 0.0);
+        for (int tid = 0; tid < nth; tid++)
+            for (long long e = tid; e < total; e += nth) red[tid] += epi_fir(p, b, (int)(e % p.nch), e / p.nch);
+        for (int s = nth / 2; s > 0; s >>= 1)
+            for (int tid = 0; tid < s; tid++) red[tid] += red[tid + s];
+        const double mean = red[0] / (double)total;
+        if (p.deemph) {
+            const int K = p.ntaps - 1;
+            for (int e = 0; e < K * p.nch; e++)
+                p.zi_next[(long long)b * p.nch * K + e] = epi_next_state(p, b, e / K, e % K);
+        }
+        for (long long e = 0; e < total; e++)
+            p.out[(long long)b * total + e] = epi_finish(p, epi_fir(p, b, (int)(e % p.nch), e / p.nch), mean);
+    }
+    (void)stream;
+    return cudaSuccess;
+#else
+    if (batch <= 0) return cudaSuccess;
+    epilogue_kernel<<<batch, kEpiThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+#endif
+}
+
+}  // namespace rc

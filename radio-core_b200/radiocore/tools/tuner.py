@@ -1,0 +1,232 @@
+"""Multi-channel tuner (mirror of radiocore/tools/tuner.py:9-174).
+
+Host side: the channel registry and the band plan.  Device side (C ABI,
+``rc_engine_*``): ``load`` is one N-point forward FFT of the one-second block;
+each channel is then the inverse B-point FFT of B+1 gathered, Hann-weighted
+bins.  Because ``add_channel`` receives the demodulator instance, ``load``
+knows every channel's chain, and the first ``demodulator.run(tuner.run(i))``
+after a ``load`` computes *all* channels' audio with batched kernels; the
+per-channel calls of ``examples/multi_fm_server.py:100-106`` then just pick up
+their slice.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+import torch
+
+from radiocore import _device, _native
+from radiocore.analog._demod import ChannelView, DemodBase
+
+MODE_NONE = 3
+
+
+@dataclass
+class Channel:
+    """Frequency boundaries and demodulator of one registered channel."""
+    index: int
+    bandwidth: float
+    demodulator: None
+    lower_frequency: float
+    center_frequency: float
+    higher_frequency: float
+
+    @property
+    def address_bytes(self) -> bytes:
+        """Little-endian int32 centre frequency: the ZeroMQ topic of the channel."""
+        return int(self.center_frequency).to_bytes(4, byteorder="little")
+
+
+class Tuner:
+    """Channelise one-second blocks of wideband IQ into the registered channels."""
+
+    def __init__(self, cuda: bool = False):
+        self._cuda = cuda
+        self._input_frequency = 0.0
+        self._input_bandwidth = 0.0
+        self._bounds: List[Channel] = []
+        self._engine = None
+        self._engine_key = None
+        self._layout = []
+        self._audio_dev = None
+        self._audio_host = None
+        self._serial = 0
+        self._audio_serial = -1
+        self._host_serial = -1
+        self._input_ref = None
+
+    # ------------------------------------------------------------ band plan
+    @property
+    def input_frequency(self) -> float:
+        """Centre frequency the wideband input must be tuned to."""
+        return self._input_frequency
+
+    @property
+    def input_bandwidth(self) -> float:
+        """Bandwidth (= samples per one-second block) of the wideband input."""
+        return self._input_bandwidth
+
+    def channels(self) -> List[Channel]:
+        return self._bounds
+
+    def request_bandwidth(self, bandwidth: float):
+        """Widen the input bandwidth (e.g. to the SDR's fixed rate); never narrows."""
+        if bandwidth < self._input_bandwidth:
+            raise ValueError(f"requested bandwidth ({bandwidth}) is too low, "
+                             f"minimum is {self._input_bandwidth}")
+        self._input_bandwidth = bandwidth
+
+    def add_channel(self, frequency: float, bandwidth: float, demodulator):
+        half = bandwidth / 2
+        self._bounds.append(Channel(len(self._bounds), bandwidth, demodulator,
+                                    frequency - half, frequency, frequency + half))
+        self._replan()
+
+    def reset(self):
+        """Forget all channels (the reference's reset raises on the empty plan,
+        tuner.py:121-124,164; here it simply returns to the initial state)."""
+        self._bounds = []
+        self._input_frequency = 0.0
+        self._input_bandwidth = 0.0
+        self._drop_engine()
+
+    def _replan(self):
+        edges_lo = [c.lower_frequency for c in self._bounds]
+        edges_hi = [c.higher_frequency for c in self._bounds]
+        lo, hi = min(edges_lo), max(edges_hi)
+        self._input_frequency = (lo + hi) / 2
+        span = hi - lo
+        # pad the span up to a multiple of the (floored) mean channel bandwidth
+        mean_bw = sum(c.bandwidth for c in self._bounds) // len(self._bounds)
+        self._input_bandwidth = span + (-span) % mean_bw
+
+    # --------------------------------------------------------------- engine
+    def _drop_engine(self):
+        h, self._engine = self._engine, None
+        self._engine_key = None
+        if h is not None:
+            try:
+                _native.lib().rc_engine_destroy(h)
+            except Exception:
+                pass
+
+    def __del__(self):
+        self._drop_engine()
+
+    def _spec(self):
+        n = int(self._input_bandwidth)
+        spec = []
+        for ch in self._bounds:
+            d = ch.demodulator
+            roll = int(self._input_frequency - ch.center_frequency) % n
+            if isinstance(d, DemodBase) and d._input_size == int(ch.bandwidth):
+                spec.append((roll, int(ch.bandwidth), d._output_size, d._mode, d._deemphasis_rate))
+            else:
+                spec.append((roll, int(ch.bandwidth), 2, MODE_NONE, 75e-6))
+        return n, tuple(spec)
+
+    def _ensure_engine(self):
+        if not self._bounds:
+            raise ValueError("no channels registered")
+        key = self._spec()
+        if self._engine is not None and key == self._engine_key:
+            return
+        self._drop_engine()
+        lib = _native.lib()
+        n, spec = key
+        h = C.c_void_p()
+        _native.check(lib.rc_engine_create(_device.device_index(), n, C.byref(h)))
+        try:
+            for roll, bw, audio, mode, tau in spec:
+                _native.check(lib.rc_engine_add_channel(h, roll, bw, audio, mode, tau, None))
+            _native.check(lib.rc_engine_commit(h))
+        except Exception:
+            lib.rc_engine_destroy(h)
+            raise
+        self._engine, self._engine_key = h, key
+        total = C.c_int64()
+        _native.check(lib.rc_engine_audio_floats(h, C.byref(total)))
+        self._audio_dev = torch.empty(max(total.value, 1), dtype=torch.float32, device="cuda")
+        self._audio_host = torch.empty(max(total.value, 1), dtype=torch.float32).pin_memory()
+        self._layout = []
+        for i in range(len(spec)):
+            off, size, nch = C.c_int64(), C.c_int64(), C.c_int()
+            _native.check(lib.rc_engine_channel_layout(h, i, C.byref(off), C.byref(size), C.byref(nch)))
+            self._layout.append((off.value, size.value, nch.value))
+
+    # ------------------------------------------------------------- hot path
+    def load(self, input_signal):
+        """Forward FFT of one second of wideband IQ (complex64, len == input_bandwidth)."""
+        self._ensure_engine()
+        if len(input_signal) != int(self._input_bandwidth):
+            raise ValueError("input_signal size and input_bandwidth mismatch")
+        x = _device.to_device(input_signal, torch.complex64)
+        self._input_ref = x
+        _native.check(_native.lib().rc_engine_load(self._engine, x.data_ptr(), _device.stream_ptr()))
+        self._serial += 1
+
+    def run(self, channel_index: int):
+        """Channel ``channel_index`` of the loaded block, as a lazy ChannelView."""
+        ch = self._bounds[int(channel_index)]
+        if self._engine is None or self._serial == 0:
+            raise RuntimeError("Tuner.load must be called before Tuner.run")
+        return ChannelView(self, ch.index, self._serial, int(ch.bandwidth))
+
+    def run_all(self, numpy_output: bool = False):
+        """All channels' audio of the loaded block in one batched pass.
+
+        Returns the packed float32 buffer (CUDA tensor, or pinned host tensor's
+        NumPy view); ``audio_slices()`` gives each channel's (offset, size, nch).
+        """
+        self._compute_audio()
+        if not numpy_output:
+            return self._audio_dev
+        self._fetch_host()
+        return self._audio_host.numpy()
+
+    def audio_slices(self):
+        self._ensure_engine()
+        return list(self._layout)
+
+    def _compute_audio(self):
+        if self._audio_serial == self._serial:
+            return
+        if self._engine is None or self._serial == 0:
+            raise RuntimeError("Tuner.load must be called before the channels are demodulated")
+        _native.check(_native.lib().rc_engine_run(self._engine, self._audio_dev.data_ptr(),
+                                                  _device.stream_ptr()))
+        self._audio_serial = self._serial
+
+    def _fetch_host(self):
+        if self._host_serial == self._serial:
+            return
+        self._audio_host.copy_(self._audio_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self._host_serial = self._serial
+
+    def _channel_iq(self, index, serial):
+        if serial != self._serial:
+            raise RuntimeError("stale channel view: Tuner.load was called again")
+        bw = int(self._bounds[index].bandwidth)
+        out = torch.empty(bw, dtype=torch.complex64, device="cuda")
+        _native.check(_native.lib().rc_engine_channel_iq(self._engine, index, out.data_ptr(),
+                                                         _device.stream_ptr()))
+        return out
+
+    def _audio_for(self, view, demod, numpy_output):
+        """Audio of ``view``'s channel if ``demod`` is the instance registered for it."""
+        if view.tuner is not self or view.serial != self._serial:
+            return None
+        ch = self._bounds[view.index]
+        off, size, nch = self._layout[view.index]
+        if ch.demodulator is not demod or nch == 0:
+            return None
+        self._compute_audio()
+        if numpy_output:
+            self._fetch_host()
+            flat = self._audio_host.numpy()[off: off + size * nch]
+            a = flat.reshape(size, nch).copy()
+            return a[None] if nch == 2 else a
+        a = self._audio_dev[off: off + size * nch].view(size, nch)
+        return a.unsqueeze(0) if nch == 2 else a

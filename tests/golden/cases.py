@@ -29,9 +29,9 @@ def pin(a, limit=4096):
 
 
 def _f64(a):
+    if hasattr(a, "detach"):                 # torch tensor (possibly on the GPU)
+        a = a.detach().cpu().numpy()
     a = np.asarray(a)
-    if hasattr(a, "get"):
-        a = a.get()
     return pin(a.astype(np.complex128 if np.iscomplexobj(a) else np.float64))
 
 

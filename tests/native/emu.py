@@ -1,0 +1,246 @@
+"""ctypes + NumPy binding of the CPU *replay* build of the kernels
+(tests/native/_build/librc_emulate.so, compiled with -DRC_EMULATE).
+
+TEST INFRASTRUCTURE ONLY: it lets the GPU-less build container run the exact
+per-thread code of every kernel (serially, on host memory) against the oracle.
+The product package never loads this library.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+BUILD = os.path.join(ROOT, "tests", "native", "_build")
+LIB = os.path.join(BUILD, "librc_emulate.so")
+SRC = os.path.join(ROOT, "radio-core_b200", "csrc")
+
+
+def build(force=False):
+    srcs = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(ROOT, "include", "radiocore_b200.h")]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    cmd = ["nvcc", "-DRC_EMULATE", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+           "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"),
+           os.path.join(SRC, "rc_engine.cu"), "-o", LIB]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.rc_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise ValueError(lib().rc_last_error().decode())
+    return rc
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _c64(x):
+    return np.ascontiguousarray(np.asarray(x), dtype=np.complex64)
+
+
+def _f32(x):
+    return np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+
+
+class _Demod:
+    mode = 0
+    channels = 1
+
+    def __init__(self, input_size, output_size, deemphasis=75e-6, cuda=False):
+        self._input_size, self._output_size = int(input_size), int(output_size)
+        self._tau = deemphasis
+        self._h = C.c_void_p()
+        _check(lib().rc_demod_create(0, self.mode, C.c_int64(self._input_size), C.c_int64(self._output_size),
+                                     C.c_double(deemphasis), 1, C.byref(self._h)))
+
+    def run(self, x, numpy_output=True):
+        if len(x) != self._input_size:
+            raise ValueError("input_sig size and input_size mismatch")
+        x = _c64(x)
+        out = np.zeros((self._output_size, self.channels), dtype=np.float32)
+        _check(lib().rc_demod_run(self._h, _p(x), _p(out), None))
+        return out[None] if self.channels == 2 else out
+
+
+class FM(_Demod):
+    mode = 0
+
+
+class MFM(_Demod):
+    mode = 1
+
+
+class WBFM(_Demod):
+    mode = 2
+    channels = 2
+
+
+class Decimate:
+    def __init__(self, input_size, output_size, cuda=False):
+        self._in, self._out = int(input_size), int(output_size)
+        self._h = C.c_void_p()
+        _check(lib().rc_decimate_create(0, C.c_int64(self._in), C.c_int64(self._out), C.byref(self._h)))
+
+    def run(self, x):
+        if len(x) != self._in:
+            raise ValueError("input_sig size and input_size mismatch")
+        x = np.asarray(x)
+        if np.iscomplexobj(x):
+            x = _c64(x)
+            out = np.zeros(self._out, dtype=np.complex64)
+            _check(lib().rc_decimate_run_complex(self._h, _p(x), _p(out), None))
+        else:
+            x = _f32(x)
+            out = np.zeros(self._out, dtype=np.float32)
+            _check(lib().rc_decimate_run_real(self._h, _p(x), _p(out), None))
+        return out
+
+
+class Deemphasis:
+    def __init__(self, input_size, rate=75e-6, dtype="float32", cuda=False):
+        self._n = int(input_size)
+        self._h = C.c_void_p()
+        _check(lib().rc_deemph_create(0, C.c_int64(self._n), C.c_double(rate), C.byref(self._h)))
+
+    def run(self, x):
+        if len(x) != self._n:
+            raise ValueError("input_sig size and input_size mismatch")
+        x = _f32(x)
+        out = np.zeros(self._n, dtype=np.float32)
+        _check(lib().rc_deemph_run(self._h, _p(x), _p(out), None))
+        return out
+
+
+class Bandpass:
+    def __init__(self, input_size, start_freq, stop_freq, dtype="float32", num_taps=61, window="hamm", cuda=False):
+        self._n = int(input_size)
+        self._h = C.c_void_p()
+        _check(lib().rc_bandpass_create(0, C.c_int64(self._n), C.c_double(start_freq), C.c_double(stop_freq),
+                                        int(num_taps), window.encode(), C.byref(self._h)))
+
+    def run(self, x):
+        if len(x) != self._n:
+            raise ValueError("input_sig size and input_size mismatch")
+        x = _f32(x)
+        out = np.zeros(self._n, dtype=np.float32)
+        _check(lib().rc_bandpass_run(self._h, _p(x), _p(out), None))
+        return out
+
+
+class PLL:
+    def __init__(self, cuda=False):
+        self._h = None
+        self._n = 0
+
+    def step(self, sig):
+        sig = _f32(sig)
+        if self._h is None or self._n != len(sig):
+            self._h = C.c_void_p()
+            self._n = len(sig)
+            _check(lib().rc_pll_create(0, C.c_int64(self._n), C.byref(self._h)))
+        _check(lib().rc_pll_step(self._h, _p(sig), None))
+
+    def _eval(self, mult, imag):
+        out = np.zeros(self._n, dtype=np.float32)
+        _check(lib().rc_pll_eval(self._h, C.c_double(mult), imag, _p(out), None))
+        return out
+
+    def real(self, mult=1.0):
+        return self._eval(mult, 0)
+
+    def image(self, mult=1.0):
+        return self._eval(mult, 1)
+
+
+class _Channel:
+    def __init__(self, index, bandwidth, demodulator, center):
+        self.index, self.bandwidth, self.demodulator, self.center_frequency = index, bandwidth, demodulator, center
+        self.lower_frequency, self.higher_frequency = center - bandwidth / 2, center + bandwidth / 2
+
+
+class Tuner:
+    """Minimal host mirror: band plan as tuner.py:163-174, arithmetic in the replay lib."""
+
+    def __init__(self, cuda=False):
+        self._bounds = []
+        self.input_frequency = 0.0
+        self.input_bandwidth = 0.0
+        self._eng = None
+        self._audio = None
+
+    def channels(self):
+        return self._bounds
+
+    def add_channel(self, frequency, bandwidth, demodulator):
+        self._bounds.append(_Channel(len(self._bounds), bandwidth, demodulator, frequency))
+        lo = min(c.lower_frequency for c in self._bounds)
+        hi = max(c.higher_frequency for c in self._bounds)
+        self.input_frequency = (lo + hi) / 2
+        self.input_bandwidth = hi - lo
+        mean_bw = sum(c.bandwidth for c in self._bounds) // len(self._bounds)
+        self.input_bandwidth += (self.input_bandwidth * -1) % mean_bw
+
+    def request_bandwidth(self, bw):
+        if bw < self.input_bandwidth:
+            raise ValueError("requested bandwidth is too low")
+        self.input_bandwidth = bw
+
+    def _commit(self):
+        N = int(self.input_bandwidth)
+        self._eng = C.c_void_p()
+        _check(lib().rc_engine_create(0, C.c_int64(N), C.byref(self._eng)))
+        for ch in self._bounds:
+            d = ch.demodulator
+            roll = int(self.input_frequency - ch.center_frequency) % N
+            mode = d.mode if d is not None else 3          # RC_MODE_NONE: IQ only
+            A = d._output_size if d is not None else 2
+            tau = d._tau if d is not None else 75e-6
+            idx = C.c_int()
+            _check(lib().rc_engine_add_channel(self._eng, C.c_int64(roll), C.c_int64(int(ch.bandwidth)),
+                                               C.c_int64(A), mode, C.c_double(tau), C.byref(idx)))
+        _check(lib().rc_engine_commit(self._eng))
+        tot = C.c_int64()
+        _check(lib().rc_engine_audio_floats(self._eng, C.byref(tot)))
+        self._audio = np.zeros(tot.value, dtype=np.float32)
+
+    def load(self, x):
+        if self._eng is None:
+            self._commit()
+        x = _c64(x)
+        if len(x) != int(self.input_bandwidth):
+            raise ValueError("input size mismatch")
+        _check(lib().rc_engine_load(self._eng, _p(x), None))
+        self._fresh = False
+
+    def run(self, index):
+        B = int(self._bounds[index].bandwidth)
+        out = np.zeros(B, dtype=np.complex64)
+        _check(lib().rc_engine_channel_iq(self._eng, int(index), _p(out), None))
+        return out
+
+    def run_all(self):
+        """Fused path: every channel's audio in one call (state carried in the engine)."""
+        _check(lib().rc_engine_run(self._eng, _p(self._audio), None))
+        res = []
+        for i in range(len(self._bounds)):
+            off, A, nch = C.c_int64(), C.c_int64(), C.c_int()
+            _check(lib().rc_engine_channel_layout(self._eng, i, C.byref(off), C.byref(A), C.byref(nch)))
+            a = self._audio[off.value: off.value + A.value * nch.value].reshape(A.value, nch.value).copy()
+            res.append(a[None] if nch.value == 2 else a)
+        return res

@@ -1,0 +1,158 @@
+"""GPU parity tests proper: the CUDA kernels, called through the C ABI by the
+drop-in ``radiocore`` classes, against (a) the committed outputs of the real
+reference and (b) the oracle on seeded inputs at larger sizes."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import radiocore_oracle as oracle
+from bench_support import synth
+from tests import parity
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
+LOOSE = {"bandpass_pll": 8.0, "decimate": 2.0}
+
+
+@pytest.fixture(scope="module")
+def rc():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import radiocore
+    assert radiocore.HasCuda()
+    return radiocore
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_cuda_matches_reference_golden(rc, name):
+    res = cases.CASES[name](rc, np)
+    for key, val in res.items():
+        ref = GOLDEN[f"{name}/{key}"]
+        if key == "f_in":
+            assert np.array_equal(ref, val)
+            continue
+        parity.assert_parity(val, ref, f"{name}/{key}", tol_scale=LOOSE.get(name, 1.0))
+
+
+@pytest.mark.parametrize("n,batch", [(1, 2), (2, 3), (30, 4), (625, 3), (1000, 2), (4800, 2), (24000, 2),
+                                     (25000, 2), (250000, 1), (1000000, 1), (2500000, 1), (10000000, 1)])
+def test_fft_engine_vs_numpy(rc, n, batch):
+    import torch
+    from radiocore import _native
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    for sign in (-1, 1):
+        out = torch.empty_like(xd)
+        _native.check(_native.lib().rc_fft_c2c(0, n, batch, sign, xd.data_ptr(), out.data_ptr(), None))
+        torch.cuda.synchronize()
+        ref = np.fft.fft(x.astype(np.complex128), axis=1) if sign < 0 else np.fft.ifft(x.astype(np.complex128), axis=1) * n
+        err = np.max(np.abs(out.cpu().numpy() - ref)) / np.sqrt(np.mean(np.abs(ref) ** 2))
+        assert err < 3e-6, (n, sign, err)
+
+
+def _pair(rc, N, B, A, C_, kind, offs=None, f0=100e6):
+    offs = synth.tiling_centers(N, C_, B) if offs is None else offs
+    g, o = rc.Tuner(cuda=True), oracle.Tuner()
+    for off in offs:
+        g.add_channel(f0 + off, B, getattr(rc, kind)(B, A, cuda=True))
+        o.add_channel(f0 + off, B, getattr(oracle, kind)(B, A))
+    g.request_bandwidth(N)
+    o.request_bandwidth(N)
+    return g, o, offs
+
+
+def test_config2_tuner_32_mfm(rc):
+    """BASELINE config 2: 10 MHz -> 32 x 250 kHz -> MFM 48 kHz, two blocks, every channel."""
+    N, B, A, C_ = 10_000_000, 250_000, 48_000, 32
+    offs = [-4e6 + 125e3 + c * 250e3 for c in range(C_)]
+    g, o, _ = _pair(rc, N, B, A, C_, "MFM", offs)
+    worst = 0.0
+    for blk in range(2):
+        x = synth.wideband(N, offs, B, seed=42, block=blk)
+        g.load(x)
+        o.load(x)
+        for ch in g.channels():
+            got = ch.demodulator.run(g.run(ch.index))
+            ref = o.channels()[ch.index].demodulator.run(o.run(ch.index))
+            assert got.shape == (A, 1) and got.dtype == np.float32
+            worst = max(worst, parity.assert_parity(got, ref, f"cfg2 b{blk} ch{ch.index}"))
+    print("config2 worst rel err", worst)
+
+
+def test_config4_wbfm_stereo(rc):
+    """BASELINE config 4 (8 of the 64 stereo channels, N scaled to 2 MHz): WBFM 250k -> 48k."""
+    N, B, A, C_ = 2_000_000, 250_000, 48_000, 8
+    g, o, offs = _pair(rc, N, B, A, C_, "WBFM")
+    worst = 0.0
+    for blk in range(2):
+        x = synth.wideband(N, offs, B, seed=4, stereo=True, block=blk)
+        g.load(x)
+        o.load(x)
+        for ch in g.channels():
+            got = ch.demodulator.run(g.run(ch.index))
+            ref = o.channels()[ch.index].demodulator.run(o.run(ch.index))
+            assert got.shape == (1, A, 2)
+            worst = max(worst, parity.assert_parity(got, ref, f"cfg4 b{blk} ch{ch.index}"))
+    print("config4 worst rel err", worst)
+
+
+def test_config1_decimate_wbfm(rc):
+    """BASELINE config 1 plumbing (examples/receive_fm.py:76-82,100-101): Decimate 2.5M->250k, WBFM ->48k."""
+    n_in, B, A = 2_500_000, 250_000, 48_000
+    x = synth.station(n_in, n_in, 0, offset_hz=12_345.0, deviation=75e3, stereo=True)
+    rng = np.random.default_rng(1234)
+    x = (x + 0.02 * (rng.standard_normal(n_in) + 1j * rng.standard_normal(n_in))).astype(np.complex64)
+    gd, gw = rc.Decimate(n_in, B, cuda=True), rc.WBFM(B, A, cuda=True)
+    od, ow = oracle.Decimate(n_in, B), oracle.WBFM(B, A)
+    iq_g, iq_o = gd.run(x), od.run(x)
+    parity.assert_parity(iq_g.cpu().numpy(), iq_o, "decimate 2.5M->250k")
+    parity.assert_parity(gw.run(iq_g), ow.run(iq_o), "wbfm after decimate")
+
+
+def test_config3_shape_fm_1m_channels(rc):
+    """BASELINE config 3 geometry scaled to 16 channels: N=16e6, B=1e6, FM(1e6 -> 48e3), full oracle."""
+    N, B, A, C_ = 16_000_000, 1_000_000, 48_000, 16
+    g, o, offs = _pair(rc, N, B, A, C_, "FM")
+    x = synth.wideband(N, offs, B, seed=3, deviation=75e3)
+    g.load(x)
+    o.load(x)
+    for ch in g.channels():
+        got = ch.demodulator.run(g.run(ch.index))
+        ref = o.channels()[ch.index].demodulator.run(o.run(ch.index))
+        parity.assert_parity(got, ref, f"cfg3 ch{ch.index}")
+
+
+def test_channel_iq_and_view(rc):
+    N, B, A, C_ = 400_000, 50_000, 12_000, 8
+    g, o, offs = _pair(rc, N, B, A, C_, "FM")
+    x = synth.wideband(N, offs, B, seed=9)
+    g.load(x)
+    o.load(x)
+    v = g.run(3)
+    assert len(v) == B and v.shape == (B,)
+    parity.assert_parity(np.asarray(v), o.run(3), "channel IQ")
+    dev = g.channels()[3].demodulator.run(v, numpy_output=False)
+    assert dev.is_cuda and tuple(dev.shape) == (A, 1)
+    # a foreign demodulator handed the view falls back to the standalone kernels: same numbers
+    other = rc.FM(B, A, cuda=True).run(v)
+    assert np.max(np.abs(other - dev.cpu().numpy())) <= 2e-6
+
+
+def test_errors(rc):
+    with pytest.raises(ValueError):
+        rc.FM(1000, 100).run(np.zeros(999, dtype=np.complex64))
+    with pytest.raises(ValueError):
+        rc.Decimate(1000, 100).run(np.zeros(1001))
+    with pytest.raises(ValueError):
+        rc.Deemphasis(1000).run(np.zeros(1001))
+    with pytest.raises(ValueError):
+        rc.FM(2 * 7 * 11, 14).run(np.zeros(154, dtype=np.complex64))
+    t = rc.Tuner()
+    t.add_channel(1e6, 1000, None)
+    with pytest.raises(ValueError):
+        t.request_bandwidth(10)
