@@ -107,6 +107,12 @@ int rc_pll_destroy(rc_pll* p);
 int rc_pll_step(rc_pll* p, const float* in_dev, void* stream);
 int rc_pll_eval(rc_pll* p, double mult, int imag, float* out_dev, void* stream);
 
+/* ---- per-kernel timing for bench.py: CUDA events around every launch ------ */
+int rc_profile_enable(int on);
+int rc_profile_reset(void);
+int64_t rc_profile_launches(void);          /* kernels launched since the last reset */
+int rc_profile_report(char* json_out, int capacity);   /* returns the size needed */
+
 /* ---- test hook: plain batched complex FFT (sign -1 forward, +1 inverse,
  *      unnormalised), used by the parity tests of the FFT engine itself ---- */
 int rc_fft_c2c(int device, int64_t n, int batch, int sign, const void* in_dev, void* out_dev,

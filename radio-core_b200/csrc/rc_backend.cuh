@@ -36,7 +36,8 @@ inline cudaError_t dev_copy(void* d, const void* s, size_t n, cudaMemcpyKind, cu
 inline cudaError_t dev_zero(void* d, size_t n, cudaStream_t) { memset(d, 0, n); return cudaSuccess; }
 inline cudaError_t dev_sync(cudaStream_t) { return cudaSuccess; }
 
-template <class F> cudaError_t launch_ew(long long n, int batch, const F& f, cudaStream_t) {
+template <class F> cudaError_t launch_ew(long long n, int batch, const F& f, cudaStream_t,
+                                         const char* = "ew", double = 0.0) {
     for (int b = 0; b < batch; b++)
         for (long long i = 0; i < n; i++) f(b, i);
     return cudaSuccess;
@@ -44,7 +45,7 @@ template <class F> cudaError_t launch_ew(long long n, int batch, const F& f, cud
 
 template <int SIGN, class LoadOp, class StoreOp>
 cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const StoreOp& st,
-                     float2* work0, float2* work1, cudaStream_t) {
+                     float2* work0, float2* work1, cudaStream_t, const char* = "fft", double = 0.0, double = 0.0) {
     for (int i = 0; i < plan.npass; i++) {
         const FftPass& P = plan.pass[i];
         const bool first = i == 0, last = i == plan.npass - 1;
@@ -94,8 +95,10 @@ template <class F> __global__ void __launch_bounds__(256) ew_kernel(const F f, l
 
 // Elementwise launch: f(batch, i) for i in [0, n).  Grid is sized in whole
 // waves of the 148 SMs (8 resident 256-thread CTAs each) and grid-strided.
-template <class F> cudaError_t launch_ew(long long n, int batch, const F& f, cudaStream_t stream) {
+template <class F> cudaError_t launch_ew(long long n, int batch, const F& f, cudaStream_t stream,
+                                         const char* tag = "ew", double bytes = 0.0) {
     if (n <= 0 || batch <= 0) return cudaSuccess;
+    ProfileScope scope(tag, bytes, stream);
     long long blocks = (n + 255) / 256;
     long long cap = (148LL * 8 * 4 + batch - 1) / batch;
     if (cap < 1) cap = 1;

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -235,33 +236,38 @@ struct DemodBank {
 
     // y: [batch][B] complex64;  out: [batch][A][nch] float32
     int run(const float2* y, float* out, cudaStream_t st) {
-        RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadDiscriminatorPacked{y, B}, StoreC64{Z1, h, 1.0f}, w0, w1, st)),
-                    "fft discriminator");
+        RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadDiscriminatorPacked{y, B}, StoreC64{Z1, h, 1.0f}, w0, w1, st,
+                              "demod.rfft_disc", 8.0 * B * batch, 0.0)), "fft discriminator");
         if (mode != RC_MODE_WBFM) {
-            RC_API_CUDA(launch_ew(hp, batch, SpecResampleEw{specBA, Z1, ZpA}, st), "spec B->A");
+            RC_API_CUDA(launch_ew(hp, batch, SpecResampleEw{specBA, Z1, ZpA}, st, "demod.spec_resample",
+                                  24.0 * hp * batch), "spec B->A");
             float* dst = mode == RC_MODE_FM ? out : audio_tmp;
-            RC_API_CUDA((fft_exec<+1>(planAh, batch, LoadC64{ZpA, hp}, StoreC64{(float2*)dst, hp, 1.0f}, w0, w1, st)),
-                        "ifft audio");
+            RC_API_CUDA((fft_exec<+1>(planAh, batch, LoadC64{ZpA, hp}, StoreC64{(float2*)dst, hp, 1.0f}, w0, w1, st,
+                                  "demod.irfft_audio")), "ifft audio");
             if (mode == RC_MODE_FM) return RC_OK;
         } else {
             // mpx = FM(B, B): same-size resample = folded Hamming taper (wbfm.py:42-43,77)
-            RC_API_CUDA(launch_ew(h, batch, SpecResampleEw{specBB, Z1, ZpB}, st), "spec B->B");
-            RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreC64{(float2*)mpx, h, 1.0f}, w0, w1, st)),
-                        "ifft mpx");
+            RC_API_CUDA(launch_ew(h, batch, SpecResampleEw{specBB, Z1, ZpB}, st, "wbfm.spec_taper", 16.0 * h * batch),
+                        "spec B->B");
+            RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreC64{(float2*)mpx, h, 1.0f}, w0, w1, st,
+                                  "wbfm.irfft_mpx")), "ifft mpx");
             // pilot = Bandpass(19 kHz +- 50, 41 taps).run(mpx)   (wbfm.py:45-46,80)
-            RC_API_CUDA(launch_ew(B, batch, FiltFiltEw{mpx, pilot, d_g, B, gK}, st), "pilot filtfilt");
+            RC_API_CUDA(launch_ew(B, batch, FiltFiltEw{mpx, pilot, d_g, B, gK}, st, "wbfm.pilot_filtfilt",
+                                  8.0 * B * batch), "pilot filtfilt");
             // PLL.step (hilbert) + image(2) * mpx * 1.0175      (wbfm.py:80-83)
-            RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadC64{(const float2*)pilot, h}, StoreC64{Z2, h, 1.0f}, w0, w1, st)),
-                        "fft pilot");
-            RC_API_CUDA(launch_ew(h, batch, SpecHilbertEw{specH, Z2, ZpB}, st), "spec hilbert");
-            RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreLmrPacked{pilot, mpx, lmr, B}, w0, w1, st)),
-                        "ifft hilbert");
+            RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadC64{(const float2*)pilot, h}, StoreC64{Z2, h, 1.0f}, w0, w1, st,
+                                  "wbfm.rfft_pilot")), "fft pilot");
+            RC_API_CUDA(launch_ew(h, batch, SpecHilbertEw{specH, Z2, ZpB}, st, "wbfm.spec_hilbert", 16.0 * h * batch),
+                        "spec hilbert");
+            RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreLmrPacked{pilot, mpx, lmr, B}, w0, w1, st,
+                                  "wbfm.irfft_hilbert_lmr", 0.0, 12.0 * B * batch)), "ifft hilbert");
             // L, R = Decimate(mpx +- lmr)                        (wbfm.py:86-87)
-            RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadC64{(const float2*)lmr, h}, StoreC64{Z2, h, 1.0f}, w0, w1, st)),
-                        "fft lmr");
-            RC_API_CUDA(launch_ew(hp, batch, SpecStereoEw{specBA, Z1, Z2, ZpA}, st), "spec stereo");
-            RC_API_CUDA((fft_exec<+1>(planAh, batch * 2, LoadC64{ZpA, hp}, StoreC64{(float2*)audio_tmp, hp, 1.0f}, w0, w1, st)),
-                        "ifft audio LR");
+            RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadC64{(const float2*)lmr, h}, StoreC64{Z2, h, 1.0f}, w0, w1, st,
+                                  "wbfm.rfft_lmr")), "fft lmr");
+            RC_API_CUDA(launch_ew(hp, batch, SpecStereoEw{specBA, Z1, Z2, ZpA}, st, "wbfm.spec_stereo",
+                                  48.0 * hp * batch), "spec stereo");
+            RC_API_CUDA((fft_exec<+1>(planAh, batch * 2, LoadC64{ZpA, hp}, StoreC64{(float2*)audio_tmp, hp, 1.0f}, w0, w1, st,
+                                  "wbfm.irfft_audio")), "ifft audio LR");
         }
         EpilogueParams p;
         p.in = audio_tmp; p.out = out; p.zi = d_zi; p.zi_next = d_zi_next; p.taps = d_taps;
@@ -429,7 +435,7 @@ int rc_engine_load(rc_engine* e, const void* iq_dev, void* stream) {
     DeviceGuard g(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     RC_API_CUDA((fft_exec<-1>(e->planN, 1, LoadC64{(const float2*)iq_dev, e->N}, StoreC64{e->X, e->N, 1.0f},
-                              e->wN0, e->wN1, st)), "tuner load fft");
+                              e->wN0, e->wN1, st, "tuner.load_fft")), "tuner load fft");
     e->loaded = true;
     return RC_OK;
 }
@@ -454,7 +460,7 @@ int rc_engine_run(rc_engine* e, float* audio_dev, void* stream) {
         const long long B = bk.demod.B;
         const int batch = bk.demod.batch;
         RC_API_CUDA((fft_exec<+1>(*bk.planB, batch, tuner_gather(e, bk.d_roll, B), StoreC64{bk.y, B, 1.0f},
-                                  bk.w0, bk.w1, st)), "tuner channel ifft");
+                                  bk.w0, bk.w1, st, "tuner.channel_ifft")), "tuner channel ifft");
         int rc = bk.demod.run(bk.y, audio_dev + bk.audio_offset, st);
         if (rc) return rc;
     }
@@ -779,6 +785,53 @@ int rc_pll_eval(rc_pll* p, double mult, int imag, float* outp, void* stream) {
     DeviceGuard g(p->device);
     RC_API_CUDA(launch_ew(p->n, 1, PllEvalEw{p->z, outp, p->n, (float)mult, imag}, (cudaStream_t)stream), "pll eval");
     return RC_OK;
+}
+
+// ------------------------------------------------------------------ profiling
+int rc_profile_enable(int on) {
+    Profiler& p = profiler();
+    p.on = on != 0;
+    return RC_OK;
+}
+int64_t rc_profile_launches(void) { return (int64_t)profiler().launches; }
+int rc_profile_reset(void) {
+    Profiler& p = profiler();
+#ifndef RC_EMULATE
+    for (auto& r : p.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+#endif
+    p.recs.clear();
+    p.launches = 0;
+    return RC_OK;
+}
+// JSON: {"tag": {"count": n, "total_ms": t, "bytes_per_launch": b}, ...}; returns the length needed.
+int rc_profile_report(char* buf, int capacity) {
+    Profiler& p = profiler();
+    std::map<std::string, std::pair<int, std::pair<double, double>>> agg;   // count, (ms, bytes)
+    std::vector<std::string> order;
+#ifndef RC_EMULATE
+    for (auto& r : p.recs) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+        if (!agg.count(r.tag)) order.push_back(r.tag);
+        auto& a = agg[r.tag];
+        a.first += 1; a.second.first += ms; a.second.second = r.bytes;
+    }
+#endif
+    std::string out = "{";
+    for (size_t i = 0; i < order.size(); i++) {
+        auto& a = agg[order[i]];
+        char line[256];
+        snprintf(line, sizeof(line), "%s\"%s\": {\"count\": %d, \"total_ms\": %.6f, \"bytes_per_launch\": %.1f}",
+                 i ? ", " : "", order[i].c_str(), a.first, a.second.first, a.second.second);
+        out += line;
+    }
+    out += "}";
+    if (buf && capacity > 0) {
+        strncpy(buf, out.c_str(), (size_t)capacity - 1);
+        buf[capacity - 1] = 0;
+    }
+    return (int)out.size() + 1;
 }
 
 // ----------------------------------------------------------------- FFT hook

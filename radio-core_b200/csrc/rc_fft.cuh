@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -164,6 +165,45 @@ template <int SIGN> struct Dft<8, SIGN> { static RC_HD void run(float2* v) { dft
 template <int SIGN> struct Dft<10, SIGN> { static RC_HD void run(float2* v) { dft_composite<2, 5, SIGN>(v); } };
 template <int SIGN> struct Dft<16, SIGN> { static RC_HD void run(float2* v) { dft_composite<4, 4, SIGN>(v); } };
 template <int SIGN> struct Dft<25, SIGN> { static RC_HD void run(float2* v) { dft_composite<5, 5, SIGN>(v); } };
+
+// ---------------------------------------------------------------------------
+// Optional per-kernel timing (rc_profile_*): CUDA events recorded on the launch
+// stream around every kernel, aggregated by kernel tag.  `bytes` is the
+// kernel's compulsory HBM traffic (its own reads + writes, each element once).
+// ---------------------------------------------------------------------------
+struct ProfileRecord { std::string tag; double bytes; cudaEvent_t a, b; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfileRecord> recs;
+    long long launches = 0;          // counted even when timing is off
+};
+inline Profiler& profiler() { static Profiler p; return p; }
+
+struct ProfileScope {
+    cudaStream_t st;
+    bool live = false;
+    ProfileScope(const char* tag, double bytes, cudaStream_t stream) : st(stream) {
+        Profiler& p = profiler();
+        p.launches++;
+#ifndef RC_EMULATE
+        if (p.on) {
+            ProfileRecord r;
+            r.tag = tag; r.bytes = bytes;
+            cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+            cudaEventRecord(r.a, st);
+            p.recs.push_back(r);
+            live = true;
+        }
+#else
+        (void)tag; (void)bytes;
+#endif
+    }
+    ~ProfileScope() {
+#ifndef RC_EMULATE
+        if (live) cudaEventRecord(profiler().recs.back().b, st);
+#endif
+    }
+};
 
 // --------------------------------------------------------------- pass record
 constexpr int kMaxStages = 16;
@@ -529,10 +569,15 @@ inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store)
 #if defined(__CUDACC__) && !defined(RC_EMULATE)
 // Run all passes.  work0/work1: scratch of batch*n float2 each (needed when
 // npass >= 2 / npass == 3).  LoadOp feeds pass 0, StoreOp drains the last pass.
+// tag / in_bytes / out_bytes feed the optional profiler: compulsory bytes the
+// first pass reads through LoadOp and the last pass writes through StoreOp
+// (0 -> 8 bytes per element, i.e. a plain complex64 array).
 template <int SIGN, class LoadOp, class StoreOp>
 cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const StoreOp& st,
-                     float2* work0, float2* work1, cudaStream_t stream) {
+                     float2* work0, float2* work1, cudaStream_t stream, const char* tag = "fft",
+                     double in_bytes = 0.0, double out_bytes = 0.0) {
     if (batch <= 0) return cudaSuccess;
+    const double plain = 8.0 * (double)plan.n * (double)batch;
     for (int i = 0; i < plan.npass; i++) {
         const FftPass& P = plan.pass[i];
         long long tiles = (P.stride + P.T - 1) / P.T;
@@ -547,6 +592,9 @@ cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const Sto
         LoadC64 lmid{src, plan.n};
         StoreC64 smid{dst, plan.n, 1.0f};
         cudaError_t e;
+        char name[96];
+        snprintf(name, sizeof(name), "%s/pass%d_R%d", tag, i, P.R);
+        ProfileScope scope(name, ((first && in_bytes > 0) ? in_bytes : plain) + ((last && out_bytes > 0) ? out_bytes : plain), stream);
 #define RC_LAUNCH(LD, ST, ldv, stv)                                                                   \
         e = cudaFuncSetAttribute(fft_pass_kernel<LD, ST, SIGN>,                                       \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \

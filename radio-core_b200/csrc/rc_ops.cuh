@@ -449,6 +449,7 @@ inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStrea
     return cudaSuccess;
 #else
     if (batch <= 0) return cudaSuccess;
+    ProfileScope scope("demod.epilogue", 8.0 * (double)p.A * p.nch * batch, stream);
     epilogue_kernel<<<batch, kEpiThreads, 0, stream>>>(p);
     return cudaGetLastError();
 #endif

@@ -51,6 +51,10 @@ _SIGNATURES = {
     "rc_pll_destroy": ([_vp], _int),
     "rc_pll_step": ([_vp, _fp, _vp], _int),
     "rc_pll_eval": ([_vp, _dbl, _int, _fp, _vp], _int),
+    "rc_profile_enable": ([_int], _int),
+    "rc_profile_reset": ([], _int),
+    "rc_profile_launches": ([], _i64),
+    "rc_profile_report": ([C.c_char_p, _int], _int),
     "rc_fft_c2c": ([_int, _i64, _int, _int, _vp, _vp, _vp], _int),
 }
 

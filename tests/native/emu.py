@@ -19,13 +19,19 @@ SRC = os.path.join(ROOT, "radio-core_b200", "csrc")
 
 def build(force=False):
     srcs = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(ROOT, "include", "radiocore_b200.h")]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+    import hashlib
+    dg = hashlib.sha256()
+    for s_ in sorted(srcs):
+        dg.update(open(s_, "rb").read())
+    stamp = LIB + ".sha256"
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dg.hexdigest():
         return LIB
     os.makedirs(BUILD, exist_ok=True)
     cmd = ["nvcc", "-DRC_EMULATE", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
            "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"),
            os.path.join(SRC, "rc_engine.cu"), "-o", LIB]
     subprocess.run(cmd, check=True, capture_output=True)
+    open(stamp, "w").write(dg.hexdigest())
     return LIB
 
 
