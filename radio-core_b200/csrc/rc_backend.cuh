@@ -43,39 +43,6 @@ template <class F> cudaError_t launch_ew(long long n, int batch, const F& f, cud
     return cudaSuccess;
 }
 
-template <int SIGN, class LoadOp, class StoreOp>
-cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const StoreOp& st,
-                     float2* work0, float2* work1, cudaStream_t, const char* = "fft", double = 0.0, double = 0.0) {
-    for (int i = 0; i < plan.npass; i++) {
-        const FftPass& P = plan.pass[i];
-        const bool first = i == 0, last = i == plan.npass - 1;
-        float2* src = (i == 1) ? work0 : work1;
-        float2* dst = (i == 0) ? work0 : work1;
-        LoadC64 lmid{src, plan.n};
-        StoreC64 smid{dst, plan.n, 1.0f};
-        long long tiles = (P.stride + P.T - 1) / P.T;
-        std::vector<float2> sm(P.smem_elems);
-        for (int b = 0; b < batch; b++)
-            for (long long tile = 0; tile < tiles; tile++) {
-                long long j0 = tile * P.T;
-                for (int tid = 0; tid < P.threads; tid++) {
-                    if (first) fft_pass_load<LoadOp, SIGN>(sm.data(), P, ld, b, j0, tid, P.threads);
-                    else fft_pass_load<LoadC64, SIGN>(sm.data(), P, lmid, b, j0, tid, P.threads);
-                }
-                int Lprev = 1;
-                for (int s = 0; s < P.nstage; s++) {
-                    for (int tid = 0; tid < P.threads; tid++)
-                        fft_stage_dispatch<SIGN>(sm.data(), P, P.radix[s], Lprev, tid, P.threads);
-                    Lprev *= P.radix[s];
-                }
-                for (int tid = 0; tid < P.threads; tid++) {
-                    if (last) fft_pass_store<StoreOp>(sm.data(), P, st, b, j0, tid, P.threads);
-                    else fft_pass_store<StoreC64>(sm.data(), P, smid, b, j0, tid, P.threads);
-                }
-            }
-    }
-    return cudaSuccess;
-}
 #else
 constexpr bool kOnDevice = true;
 inline cudaError_t dev_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1); }

@@ -16,7 +16,7 @@
 #include <vector>
 
 #include "../../include/radiocore_b200.h"
-#include "rc_ops.cuh"
+#include "rc_exec.cuh"
 
 namespace rc {
 
@@ -352,8 +352,8 @@ int rc_engine_commit(rc_engine* e) {
     DeviceGuard g(e->device);
     RC_API_CUDA(fft_plan_build(e->planN, e->N, e->store), "plan N");
     RC_API_CUDA(e->arena.alloc(&e->X, (size_t)e->N), "alloc X");
-    if (e->planN.npass >= 2) RC_API_CUDA(e->arena.alloc(&e->wN0, (size_t)e->N), "alloc wN0");
-    if (e->planN.npass >= 3) RC_API_CUDA(e->arena.alloc(&e->wN1, (size_t)e->N), "alloc wN1");
+    if (e->planN.max_passes() >= 2) RC_API_CUDA(e->arena.alloc(&e->wN0, (size_t)e->N), "alloc wN0");
+    if (e->planN.max_passes() >= 3) RC_API_CUDA(e->arena.alloc(&e->wN1, (size_t)e->N), "alloc wN1");
     // group channels with identical demodulator configuration
     size_t maxB = 0;
     for (size_t i = 0; i < e->chans.size(); i++) {
@@ -383,8 +383,8 @@ int rc_engine_commit(rc_engine* e) {
         for (int m : bk.members) rolls.push_back(e->chans[m].roll);
         RC_API_CUDA(e->arena.upload(&bk.d_roll, rolls), "rolls");
         RC_API_CUDA(e->arena.alloc(&bk.y, (size_t)batch * c0.B), "alloc y");
-        if (bk.planB->npass >= 2) RC_API_CUDA(e->arena.alloc(&bk.w0, (size_t)batch * c0.B), "alloc yw0");
-        if (bk.planB->npass >= 3) RC_API_CUDA(e->arena.alloc(&bk.w1, (size_t)batch * c0.B), "alloc yw1");
+        if (bk.planB->max_passes() >= 2) RC_API_CUDA(e->arena.alloc(&bk.w0, (size_t)batch * c0.B), "alloc yw0");
+        if (bk.planB->max_passes() >= 3) RC_API_CUDA(e->arena.alloc(&bk.w1, (size_t)batch * c0.B), "alloc yw1");
         bk.audio_offset = off;
         off += (long long)batch * c0.A * bk.demod.nch;
     }

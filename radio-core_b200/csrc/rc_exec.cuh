@@ -1,0 +1,149 @@
+// rc_exec.cuh -- runs an FftPlan: picks the register-radix passes (rc_fft2.cuh)
+// when the plan has them and the fused load/store functors are ones those
+// kernels are instantiated for, the generic shared-memory passes otherwise.
+#pragma once
+
+#include "rc_ops.cuh"
+
+namespace rc {
+
+// ---- the functor kinds the register-radix kernels are compiled for ----------
+enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2 };
+enum { kStC64 = 0, kStLmr = 1 };
+
+struct LoadAny {
+    int kind;
+    LoadC64 c64;
+    LoadResampleGather gather;
+    LoadDiscriminatorPacked disc;
+};
+struct StoreAny {
+    int kind;
+    StoreC64 c64;
+    StoreLmrPacked lmr;
+};
+
+template <class L> struct V2LoadOk { static constexpr bool value = false; };
+template <> struct V2LoadOk<LoadC64> { static constexpr bool value = true; };
+template <> struct V2LoadOk<LoadResampleGather> { static constexpr bool value = true; };
+template <> struct V2LoadOk<LoadDiscriminatorPacked> { static constexpr bool value = true; };
+template <class S> struct V2StoreOk { static constexpr bool value = false; };
+template <> struct V2StoreOk<StoreC64> { static constexpr bool value = true; };
+template <> struct V2StoreOk<StoreLmrPacked> { static constexpr bool value = true; };
+
+inline LoadAny to_any(const LoadC64& l) { LoadAny a{}; a.kind = kLdC64; a.c64 = l; return a; }
+inline LoadAny to_any(const LoadResampleGather& l) { LoadAny a{}; a.kind = kLdGather; a.gather = l; return a; }
+inline LoadAny to_any(const LoadDiscriminatorPacked& l) { LoadAny a{}; a.kind = kLdDisc; a.disc = l; return a; }
+inline StoreAny to_any(const StoreC64& s) { StoreAny a{}; a.kind = kStC64; a.c64 = s; return a; }
+inline StoreAny to_any(const StoreLmrPacked& s) { StoreAny a{}; a.kind = kStLmr; a.lmr = s; return a; }
+
+// Defined in rc_fft2_g<k>.cu (schedule ids with id % kV2Groups == k).
+#define RC_V2_DECL(k)                                                                                         \
+    cudaError_t v2_first_g##k(int id, int sign, const FftPass& P, const LoadAny& ld, const StoreC64& st,      \
+                              int batch, cudaStream_t stream);                                                \
+    cudaError_t v2_later_g##k(int id, int sign, const FftPass& P, const LoadC64& ld, const StoreAny& st,      \
+                              int batch, cudaStream_t stream);
+RC_V2_DECL(0) RC_V2_DECL(1) RC_V2_DECL(2) RC_V2_DECL(3)
+#undef RC_V2_DECL
+
+inline cudaError_t v2_first(const FftPass& P, int sign, const LoadAny& ld, const StoreC64& st, int batch,
+                            cudaStream_t stream) {
+    switch (P.fast_id % kV2Groups) {
+        case 0: return v2_first_g0(P.fast_id, sign, P, ld, st, batch, stream);
+        case 1: return v2_first_g1(P.fast_id, sign, P, ld, st, batch, stream);
+        case 2: return v2_first_g2(P.fast_id, sign, P, ld, st, batch, stream);
+        default: return v2_first_g3(P.fast_id, sign, P, ld, st, batch, stream);
+    }
+}
+inline cudaError_t v2_later(const FftPass& P, int sign, const LoadC64& ld, const StoreAny& st, int batch,
+                            cudaStream_t stream) {
+    switch (P.fast_id % kV2Groups) {
+        case 0: return v2_later_g0(P.fast_id, sign, P, ld, st, batch, stream);
+        case 1: return v2_later_g1(P.fast_id, sign, P, ld, st, batch, stream);
+        case 2: return v2_later_g2(P.fast_id, sign, P, ld, st, batch, stream);
+        default: return v2_later_g3(P.fast_id, sign, P, ld, st, batch, stream);
+    }
+}
+
+inline bool fft_grid_dims(int batch, int& by, int& bz) {
+    by = batch; bz = 1;
+    while (by > 65535) { bz *= 2; by = (batch + bz - 1) / bz; }
+    return (long long)by * bz == batch;          // caller keeps batch <= 65535 or a multiple of the split
+}
+
+// one generic shared-memory pass (device launch or CPU replay)
+template <int SIGN, class LD, class ST>
+cudaError_t fft_generic_pass(const FftPass& P, int batch, const LD& ld, const ST& st, cudaStream_t stream) {
+#ifdef RC_EMULATE
+    (void)stream;
+    long long tiles = (P.stride + P.T - 1) / P.T;
+    std::vector<float2> sm(P.smem_elems);
+    for (int b = 0; b < batch; b++)
+        for (long long tile = 0; tile < tiles; tile++) {
+            long long j0 = tile * P.T;
+            for (int tid = 0; tid < P.threads; tid++) fft_pass_load<LD, SIGN>(sm.data(), P, ld, b, j0, tid, P.threads);
+            int Lprev = 1;
+            for (int s = 0; s < P.nstage; s++) {
+                for (int tid = 0; tid < P.threads; tid++)
+                    fft_stage_dispatch<SIGN>(sm.data(), P, P.radix[s], Lprev, tid, P.threads);
+                Lprev *= P.radix[s];
+            }
+            for (int tid = 0; tid < P.threads; tid++) fft_pass_store<ST>(sm.data(), P, st, b, j0, tid, P.threads);
+        }
+    return cudaSuccess;
+#else
+    long long tiles = (P.stride + P.T - 1) / P.T;
+    int by, bz;
+    if (!fft_grid_dims(batch, by, bz)) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)tiles, (unsigned)by, (unsigned)bz);
+    size_t smem = (size_t)P.smem_elems * sizeof(float2);
+    cudaError_t e = cudaFuncSetAttribute(fft_pass_kernel<LD, ST, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fft_pass_kernel<LD, ST, SIGN><<<grid, P.threads, smem, stream>>>(P, ld, st);
+    return cudaGetLastError();
+#endif
+}
+
+// Run all passes.  work0/work1: scratch of batch*n float2 each (work0 needed
+// when the plan has >= 2 passes, work1 when >= 3; size by plan.max_passes()).
+// LoadOp feeds pass 0, StoreOp drains the last pass.  tag / in_bytes /
+// out_bytes feed the optional profiler: compulsory bytes the first pass reads
+// through LoadOp and the last pass writes through StoreOp (0 -> 8 bytes per
+// element, i.e. a plain complex64 array).
+template <int SIGN, class LoadOp, class StoreOp>
+cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const StoreOp& st,
+                     float2* work0, float2* work1, cudaStream_t stream, const char* tag = "fft",
+                     double in_bytes = 0.0, double out_bytes = 0.0) {
+    if (batch <= 0) return cudaSuccess;
+    constexpr bool v2ok = V2LoadOk<LoadOp>::value && V2StoreOk<StoreOp>::value;
+    const bool fast = v2ok && plan.nfast >= 2;
+    const int npass = fast ? plan.nfast : plan.npass;
+    const FftPass* passes = fast ? plan.fast : plan.pass;
+    const double plain = 8.0 * (double)plan.n * (double)batch;
+    for (int i = 0; i < npass; i++) {
+        const FftPass& P = passes[i];
+        const bool first = i == 0, last = i == npass - 1;
+        float2* src = ((i - 1) % 2 == 0) ? work0 : work1;
+        float2* dst = (i % 2 == 0) ? work0 : work1;
+        LoadC64 lmid{src, plan.n};
+        StoreC64 smid{dst, plan.n, 1.0f};
+        char name[96];
+        snprintf(name, sizeof(name), "%s/pass%d_R%d%s", tag, i, P.R, fast ? "r" : "");
+        ProfileScope scope(name, ((first && in_bytes > 0) ? in_bytes : plain) + ((last && out_bytes > 0) ? out_bytes : plain), stream);
+        cudaError_t e = cudaSuccess;
+        if (fast) {
+            if constexpr (v2ok) {
+                if (first) e = v2_first(P, SIGN, to_any(ld), smid, batch, stream);
+                else if (last) e = v2_later(P, SIGN, lmid, to_any(st), batch, stream);
+                else e = v2_later(P, SIGN, lmid, to_any(smid), batch, stream);
+            }
+        } else if (first && last) e = fft_generic_pass<SIGN>(P, batch, ld, st, stream);
+        else if (first) e = fft_generic_pass<SIGN>(P, batch, ld, smid, stream);
+        else if (last) e = fft_generic_pass<SIGN>(P, batch, lmid, st, stream);
+        else e = fft_generic_pass<SIGN>(P, batch, lmid, smid, stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace rc

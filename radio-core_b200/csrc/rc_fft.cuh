@@ -37,6 +37,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -165,6 +166,10 @@ template <int SIGN> struct Dft<8, SIGN> { static RC_HD void run(float2* v) { dft
 template <int SIGN> struct Dft<10, SIGN> { static RC_HD void run(float2* v) { dft_composite<2, 5, SIGN>(v); } };
 template <int SIGN> struct Dft<16, SIGN> { static RC_HD void run(float2* v) { dft_composite<4, 4, SIGN>(v); } };
 template <int SIGN> struct Dft<25, SIGN> { static RC_HD void run(float2* v) { dft_composite<5, 5, SIGN>(v); } };
+template <int SIGN> struct Dft<6, SIGN> { static RC_HD void run(float2* v) { dft_composite<2, 3, SIGN>(v); } };
+template <int SIGN> struct Dft<12, SIGN> { static RC_HD void run(float2* v) { dft_composite<4, 3, SIGN>(v); } };
+template <int SIGN> struct Dft<15, SIGN> { static RC_HD void run(float2* v) { dft_composite<3, 5, SIGN>(v); } };
+template <int SIGN> struct Dft<20, SIGN> { static RC_HD void run(float2* v) { dft_composite<4, 5, SIGN>(v); } };
 
 // ---------------------------------------------------------------------------
 // Optional per-kernel timing (rc_profile_*): CUDA events recorded on the launch
@@ -227,6 +232,7 @@ struct FftPass {
     const int* pos;        // time index t -> shared-memory slot (digit reversal)
     int threads;
     int smem_elems;
+    int fast_id;           // >= 0: register-radix schedule of rc_fft2.cuh, -1: generic kernel
 };
 
 RC_HD int fft_phys(const FftPass& P, int p, int c) {
@@ -372,8 +378,11 @@ __global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass P, const Lo
 // ------------------------------------------------------------------- planning
 struct FftPlan {
     long long n = 0;
-    int npass = 0;
+    int npass = 0;                 // generic shared-memory passes (any 2^a 3^b 5^c size)
     FftPass pass[kMaxPasses];
+    int nfast = 0;                 // register-radix passes (rc_fft2.cuh) when n splits into curated lengths
+    FftPass fast[kMaxPasses];
+    int max_passes() const { return npass > nfast ? npass : nfast; }
 };
 
 // Memory source for the plan tables: device (product) or host (CPU emulation).
@@ -470,6 +479,155 @@ inline bool fft_choose_passes(long long n, std::vector<int>& Rs, int& T) {
     return false;
 }
 
+// Fill one pass record (tables are shared through the store).  fast_id >= 0 marks a
+// register-radix pass (rc_fft2.cuh): no digit-reversal table, T = 16.
+inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long long Ns, TableStore& store, int fast_id) {
+    cudaError_t err = cudaSuccess;
+    memset(&P, 0, sizeof(P));
+    P.fast_id = fast_id;
+    P.R = R;
+    P.T = T;
+    P.logT = 0;
+    while ((1 << P.logT) < T) P.logT++;
+    std::vector<int> rad = fft_radix_schedule(P.R);
+    if (rad.size() == 1 && rad[0] == 1) rad.clear();
+    P.nstage = (int)rad.size();
+    for (int s = 0; s < P.nstage; s++) P.radix[s] = rad[s];
+    P.n = n;
+    P.Ns = Ns;
+    P.stride = n / P.R;
+    P.M = (unsigned long long)Ns * P.R;
+    // W_R table (forward)
+    {
+        std::string key = "twR:" + std::to_string(P.R);
+        if (!store.has(key)) {
+            std::vector<float2> t(P.R);
+            for (int m = 0; m < P.R; m++) {
+                long double a = -2.0L * 3.14159265358979323846264338327950288L * m / P.R;
+                t[m] = make_float2((float)cosl(a), (float)sinl(a));
+            }
+            store.put(key, t.data(), t.size() * sizeof(float2), &err);
+        }
+        P.twR = (const float2*)store.put(key, nullptr, 0, &err);
+    }
+    // digit-reversal table (generic kernel only)
+    if (fast_id < 0) {
+        std::string key = "pos:" + std::to_string(P.R);
+        if (!store.has(key)) {
+            std::vector<int> pos(P.R);
+            for (int t = 0; t < P.R; t++) {
+                int tmp = t, p = 0;
+                std::vector<int> L(P.nstage + 1, 1);
+                for (int s = 0; s < P.nstage; s++) L[s + 1] = L[s] * P.radix[s];
+                for (int s = P.nstage - 1; s >= 0; s--) {
+                    int m = tmp % P.radix[s];
+                    tmp /= P.radix[s];
+                    p += m * L[s];
+                }
+                pos[t] = p;
+            }
+            store.put(key, pos.data(), pos.size() * sizeof(int), &err);
+        }
+        P.pos = (const int*)store.put(key, nullptr, 0, &err);
+    }
+    // inter-pass twiddle tables W_M, M = Ns*R (fp64, forward)
+    if (Ns > 1) {
+        int bits = 0;
+        while ((1ULL << bits) < P.M) bits++;
+        P.tw_shift = (bits + 1) / 2;
+        P.tw_mask = (1u << P.tw_shift) - 1u;
+        std::string key = "twM:" + std::to_string(P.M);
+        if (!store.has(key + ":lo")) {
+            size_t nlo = (size_t)1 << P.tw_shift;
+            size_t nhi = (size_t)((P.M >> P.tw_shift) + 1);
+            std::vector<double2> lo(nlo), hi(nhi);
+            const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+            for (size_t q = 0; q < nlo; q++) {
+                long double a = -tau * (long double)q / (long double)P.M;
+                lo[q] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+            for (size_t q = 0; q < nhi; q++) {
+                unsigned long long qq = ((unsigned long long)q << P.tw_shift) % P.M;
+                long double a = -tau * (long double)qq / (long double)P.M;
+                hi[q] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+            store.put(key + ":lo", lo.data(), nlo * sizeof(double2), &err);
+            store.put(key + ":hi", hi.data(), nhi * sizeof(double2), &err);
+        }
+        P.tw_lo = (const double2*)store.put(key + ":lo", nullptr, 0, &err);
+        P.tw_hi = (const double2*)store.put(key + ":hi", nullptr, 0, &err);
+    }
+    P.smem_elems = T > 1 ? P.R * (T + 1) : P.R + (P.R >> 4) + 1;
+    long long work = (long long)P.R * T;
+    int th = (int)((work / 8 + 31) / 32 * 32);
+    if (th < 64) th = 64;
+    if (th > 512) th = 512;
+    P.threads = th;
+    return err;
+}
+
+// ---- register-radix schedules (rc_fft2.cuh): X(id, R0, R1, R2, threads, min CTAs/SM) ----
+// R = R0*R1*R2; R1 == 1 marks a two-stage schedule.  Kernels are instantiated in
+// rc_fft2_g*.cu, one group per translation unit (id % 4) so they compile in parallel.
+#define RC_V2_GROUP0(X) X(0, 10, 1, 10, 160, 4) X(4, 10, 1, 16, 128, 4) X(8, 4, 8, 10, 256, 2) X(12, 6, 10, 10, 320, 2) X(16, 8, 10, 10, 320, 2)
+#define RC_V2_GROUP1(X) X(1, 5, 5, 5, 400, 2) X(5, 10, 1, 20, 160, 4) X(9, 4, 10, 10, 320, 2) X(13, 5, 5, 25, 400, 1) X(17, 10, 10, 10, 400, 1)
+#define RC_V2_GROUP2(X) X(2, 8, 1, 16, 128, 4) X(6, 5, 5, 10, 400, 2) X(10, 5, 10, 10, 400, 2) X(14, 8, 8, 10, 256, 2)
+#define RC_V2_GROUP3(X) X(3, 10, 1, 15, 160, 4) X(7, 16, 1, 16, 256, 2) X(11, 8, 8, 8, 256, 2) X(15, 5, 6, 10, 160, 4)
+#define RC_V2_ALL(X) RC_V2_GROUP0(X) RC_V2_GROUP1(X) RC_V2_GROUP2(X) RC_V2_GROUP3(X)
+constexpr int kV2Groups = 4;
+
+struct V2Entry { int id, R0, R1, R2, threads; int R() const { return R0 * R1 * R2; } };
+inline const std::vector<V2Entry>& v2_table() {
+    static const std::vector<V2Entry> t = {
+#define RC_V2_ROW(id, r0, r1, r2, nt, mb) {id, r0, r1, r2, nt},
+        RC_V2_ALL(RC_V2_ROW)
+#undef RC_V2_ROW
+    };
+    return t;
+}
+inline const V2Entry* v2_find(int R) {
+    for (const V2Entry& e : v2_table()) if (e.R() == R) return &e;
+    return nullptr;
+}
+
+// Split n into 2..4 curated pass lengths; false when n has no such split.
+inline bool fft_choose_fast(long long n, std::vector<int>& Rs) {
+    std::vector<int> cur;
+    for (const V2Entry& e : v2_table()) if (n % e.R() == 0) cur.push_back(e.R());
+    double best = 1e30;
+    std::vector<int> pick;
+    auto score = [&](const std::vector<int>& r) {
+        double s = 1000.0 * r.size();
+        long long Ns = 1;
+        int maxR = 0;
+        for (size_t i = 0; i < r.size(); i++) {
+            if ((n / r[i]) % 16) s += 10;              // input rows not 128-byte aligned
+            if (i > 0 && (Ns % 16)) s += 10;           // output tiles straddle Ns blocks
+            if (r[i] > maxR) maxR = r[i];
+            Ns *= r[i];
+        }
+        return s + maxR / 100.0;
+    };
+    std::vector<int> r;
+    std::function<void(long long, int)> rec = [&](long long rest, int depth) {
+        if (rest == 1 && r.size() >= 2) {
+            double sc = score(r);
+            if (sc < best) { best = sc; pick = r; }
+            return;
+        }
+        if (depth == kMaxPasses) return;
+        for (int c : cur) {
+            if (rest % c) continue;
+            r.push_back(c);
+            rec(rest / c, depth + 1);
+            r.pop_back();
+        }
+    };
+    rec(n, 0);
+    Rs = pick;
+    return !pick.empty();
+}
+
 inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store) {
     if (!fft_size_supported(n)) return cudaErrorInvalidValue;
     std::vector<int> Rs;
@@ -478,138 +636,23 @@ inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store)
     plan.n = n;
     plan.npass = (int)Rs.size();
     long long Ns = 1;
-    cudaError_t err = cudaSuccess;
     for (int i = 0; i < plan.npass; i++) {
-        FftPass& P = plan.pass[i];
-        memset(&P, 0, sizeof(P));
-        P.R = Rs[i];
-        P.T = T;
-        P.logT = 0;
-        while ((1 << P.logT) < T) P.logT++;
-        std::vector<int> rad = fft_radix_schedule(P.R);
-        if (rad.size() == 1 && rad[0] == 1) rad.clear();
-        P.nstage = (int)rad.size();
-        for (int s = 0; s < P.nstage; s++) P.radix[s] = rad[s];
-        P.n = n;
-        P.Ns = Ns;
-        P.stride = n / P.R;
-        P.M = (unsigned long long)Ns * P.R;
-        // W_R table (forward)
-        {
-            std::string key = "twR:" + std::to_string(P.R);
-            if (!store.has(key)) {
-                std::vector<float2> t(P.R);
-                for (int m = 0; m < P.R; m++) {
-                    long double a = -2.0L * 3.14159265358979323846264338327950288L * m / P.R;
-                    t[m] = make_float2((float)cosl(a), (float)sinl(a));
-                }
-                store.put(key, t.data(), t.size() * sizeof(float2), &err);
-            }
-            P.twR = (const float2*)store.put(key, nullptr, 0, &err);
-        }
-        // digit-reversal table
-        {
-            std::string key = "pos:" + std::to_string(P.R);
-            if (!store.has(key)) {
-                std::vector<int> pos(P.R);
-                for (int t = 0; t < P.R; t++) {
-                    int tmp = t, p = 0;
-                    std::vector<int> L(P.nstage + 1, 1);
-                    for (int s = 0; s < P.nstage; s++) L[s + 1] = L[s] * P.radix[s];
-                    for (int s = P.nstage - 1; s >= 0; s--) {
-                        int m = tmp % P.radix[s];
-                        tmp /= P.radix[s];
-                        p += m * L[s];
-                    }
-                    pos[t] = p;
-                }
-                store.put(key, pos.data(), pos.size() * sizeof(int), &err);
-            }
-            P.pos = (const int*)store.put(key, nullptr, 0, &err);
-        }
-        // inter-pass twiddle tables W_M, M = Ns*R (fp64, forward)
-        if (Ns > 1) {
-            int bits = 0;
-            while ((1ULL << bits) < P.M) bits++;
-            P.tw_shift = (bits + 1) / 2;
-            P.tw_mask = (1u << P.tw_shift) - 1u;
-            std::string key = "twM:" + std::to_string(P.M);
-            if (!store.has(key + ":lo")) {
-                size_t nlo = (size_t)1 << P.tw_shift;
-                size_t nhi = (size_t)((P.M >> P.tw_shift) + 1);
-                std::vector<double2> lo(nlo), hi(nhi);
-                const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
-                for (size_t q = 0; q < nlo; q++) {
-                    long double a = -tau * (long double)q / (long double)P.M;
-                    lo[q] = make_double2((double)cosl(a), (double)sinl(a));
-                }
-                for (size_t q = 0; q < nhi; q++) {
-                    unsigned long long qq = ((unsigned long long)q << P.tw_shift) % P.M;
-                    long double a = -tau * (long double)qq / (long double)P.M;
-                    hi[q] = make_double2((double)cosl(a), (double)sinl(a));
-                }
-                store.put(key + ":lo", lo.data(), nlo * sizeof(double2), &err);
-                store.put(key + ":hi", hi.data(), nhi * sizeof(double2), &err);
-            }
-            P.tw_lo = (const double2*)store.put(key + ":lo", nullptr, 0, &err);
-            P.tw_hi = (const double2*)store.put(key + ":hi", nullptr, 0, &err);
-        }
-        P.smem_elems = T > 1 ? P.R * (T + 1) : P.R + (P.R >> 4) + 1;
-        long long work = (long long)P.R * T;
-        int th = (int)((work / 8 + 31) / 32 * 32);
-        if (th < 64) th = 64;
-        if (th > 512) th = 512;
-        P.threads = th;
+        cudaError_t err = fft_fill_pass(plan.pass[i], n, Rs[i], T, Ns, store, -1);
         if (err != cudaSuccess) return err;
-        Ns *= P.R;
+        Ns *= Rs[i];
+    }
+    plan.nfast = 0;
+    std::vector<int> Fs;
+    if (fft_choose_fast(n, Fs)) {
+        plan.nfast = (int)Fs.size();
+        Ns = 1;
+        for (int i = 0; i < plan.nfast; i++) {
+            cudaError_t err = fft_fill_pass(plan.fast[i], n, Fs[i], 16, Ns, store, v2_find(Fs[i])->id);
+            if (err != cudaSuccess) return err;
+            Ns *= Fs[i];
+        }
     }
     return cudaSuccess;
 }
-
-#if defined(__CUDACC__) && !defined(RC_EMULATE)
-// Run all passes.  work0/work1: scratch of batch*n float2 each (needed when
-// npass >= 2 / npass == 3).  LoadOp feeds pass 0, StoreOp drains the last pass.
-// tag / in_bytes / out_bytes feed the optional profiler: compulsory bytes the
-// first pass reads through LoadOp and the last pass writes through StoreOp
-// (0 -> 8 bytes per element, i.e. a plain complex64 array).
-template <int SIGN, class LoadOp, class StoreOp>
-cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const StoreOp& st,
-                     float2* work0, float2* work1, cudaStream_t stream, const char* tag = "fft",
-                     double in_bytes = 0.0, double out_bytes = 0.0) {
-    if (batch <= 0) return cudaSuccess;
-    const double plain = 8.0 * (double)plan.n * (double)batch;
-    for (int i = 0; i < plan.npass; i++) {
-        const FftPass& P = plan.pass[i];
-        long long tiles = (P.stride + P.T - 1) / P.T;
-        int by = batch, bz = 1;
-        while (by > 65535) { bz *= 2; by = (batch + bz - 1) / bz; }
-        if ((long long)by * bz != batch) return cudaErrorInvalidValue;   // caller keeps batch <= 65535 or even
-        dim3 grid((unsigned)tiles, (unsigned)by, (unsigned)bz);
-        size_t smem = (size_t)P.smem_elems * sizeof(float2);
-        const bool first = i == 0, last = i == plan.npass - 1;
-        float2* src = (i == 1) ? work0 : work1;
-        float2* dst = (i == 0) ? work0 : work1;
-        LoadC64 lmid{src, plan.n};
-        StoreC64 smid{dst, plan.n, 1.0f};
-        cudaError_t e;
-        char name[96];
-        snprintf(name, sizeof(name), "%s/pass%d_R%d", tag, i, P.R);
-        ProfileScope scope(name, ((first && in_bytes > 0) ? in_bytes : plain) + ((last && out_bytes > 0) ? out_bytes : plain), stream);
-#define RC_LAUNCH(LD, ST, ldv, stv)                                                                   \
-        e = cudaFuncSetAttribute(fft_pass_kernel<LD, ST, SIGN>,                                       \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-        if (e != cudaSuccess) return e;                                                               \
-        fft_pass_kernel<LD, ST, SIGN><<<grid, P.threads, smem, stream>>>(P, ldv, stv);
-        if (first && last) { RC_LAUNCH(LoadOp, StoreOp, ld, st) }
-        else if (first)    { RC_LAUNCH(LoadOp, StoreC64, ld, smid) }
-        else if (last)     { RC_LAUNCH(LoadC64, StoreOp, lmid, st) }
-        else               { RC_LAUNCH(LoadC64, StoreC64, lmid, smid) }
-#undef RC_LAUNCH
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
-}
-#endif
 
 }  // namespace rc

@@ -392,7 +392,7 @@ RC_HD float epi_finish(const EpilogueParams& p, double v, double mean) {
 
 #if defined(__CUDACC__) && !defined(RC_EMULATE)
 constexpr int kEpiThreads = 1024;
-__global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpilogueParams p) {
+static __global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpilogueParams p) {
     __shared__ double red[kEpiThreads];
     const int b = blockIdx.x, tid = threadIdx.x;
     const long long total = p.A * p.nch;

@@ -27,10 +27,13 @@ def build(force=False):
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dg.hexdigest():
         return LIB
     os.makedirs(BUILD, exist_ok=True)
-    cmd = ["nvcc", "-DRC_EMULATE", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-           "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"),
-           os.path.join(SRC, "rc_engine.cu"), "-o", LIB]
-    subprocess.run(cmd, check=True, capture_output=True)
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    flags = ["-DRC_EMULATE", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
+             "-I", os.path.join(ROOT, "include")]
+    g.compile_units([s_ for s_ in sorted(srcs) if s_.endswith(".cu")], flags, os.path.join(BUILD, "obj"), LIB)
     open(stamp, "w").write(dg.hexdigest())
     return LIB
 
