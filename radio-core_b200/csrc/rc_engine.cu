@@ -141,6 +141,21 @@ static std::vector<float2> unit_circle_table(long long n, long long count, int s
     return t;
 }
 
+// Hann weights of Tuner.run's gathered bins (tuner.py:155-161) for channel size B out of N:
+// entry i is W(kc) / N with kc = i (i <= B/2) or i - B, W the fftshifted periodic Hann window
+// of length N; *w_neg_half = W(-B/2) / N, the weight of the bin merged into i = B/2.
+static std::vector<float> tuner_window_table(long long N, long long B, float* w_neg_half) {
+    std::vector<float> t((size_t)B);
+    const long double phi = (N % 2 == 0) ? 0.0L : 3.14159265358979323846264338327950288L / (long double)N;
+    auto w = [&](long long kc) {
+        const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)kc / (long double)N + phi;
+        return (0.5L + 0.5L * cosl(a)) / (long double)N;
+    };
+    for (long long i = 0; i < B; i++) t[(size_t)i] = (float)w(i <= B / 2 ? i : i - B);
+    *w_neg_half = (float)w(-(B / 2));
+    return t;
+}
+
 // ------------------------------------------------------- real resampler setup
 static cudaError_t make_real_spec(RealResampleSpec& s, long long n_x, long long num, bool hamming,
                                   bool full_table, Arena& arena) {
@@ -172,6 +187,7 @@ struct DemodBank {
     float zi0[50];
     float* d_taps = nullptr;
     double* d_zi = nullptr; double* d_zi_next = nullptr;
+    double* d_stage = nullptr; double* d_partial = nullptr;
     double* d_g = nullptr; int gK = 0;
     float2 *Z1 = nullptr, *Z2 = nullptr, *ZpB = nullptr, *ZpA = nullptr, *w0 = nullptr, *w1 = nullptr;
     float *mpx = nullptr, *pilot = nullptr, *lmr = nullptr, *audio_tmp = nullptr;
@@ -202,6 +218,8 @@ struct DemodBank {
             RC_API_CUDA(arena.upload(&d_taps, t), "taps");
             RC_API_CUDA(arena.alloc(&d_zi, (size_t)batch * nch * 50), "zi");
             RC_API_CUDA(arena.alloc(&d_zi_next, (size_t)batch * nch * 50), "zi_next");
+            RC_API_CUDA(arena.alloc(&d_stage, (size_t)batch * nch * A), "stage");
+            RC_API_CUDA(arena.alloc(&d_partial, (size_t)batch * nch * epi_chunks(A)), "partial");
             int rc = reset_state();
             if (rc) return rc;
         }
@@ -252,8 +270,7 @@ struct DemodBank {
             RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreC64{(float2*)mpx, h, 1.0f}, w0, w1, st,
                                   "wbfm.irfft_mpx")), "ifft mpx");
             // pilot = Bandpass(19 kHz +- 50, 41 taps).run(mpx)   (wbfm.py:45-46,80)
-            RC_API_CUDA(launch_ew(B, batch, FiltFiltEw{mpx, pilot, d_g, B, gK}, st, "wbfm.pilot_filtfilt",
-                                  8.0 * B * batch), "pilot filtfilt");
+            RC_API_CUDA(launch_filtfilt(FiltFiltEw{mpx, pilot, d_g, B, gK}, batch, st, "wbfm.pilot_filtfilt"), "pilot filtfilt");
             // PLL.step (hilbert) + image(2) * mpx * 1.0175      (wbfm.py:80-83)
             RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadC64{(const float2*)pilot, h}, StoreC64{Z2, h, 1.0f}, w0, w1, st,
                                   "wbfm.rfft_pilot")), "fft pilot");
@@ -271,6 +288,7 @@ struct DemodBank {
         }
         EpilogueParams p;
         p.in = audio_tmp; p.out = out; p.zi = d_zi; p.zi_next = d_zi_next; p.taps = d_taps;
+        p.stage = d_stage; p.partial = d_partial;
         p.A = A; p.nch = nch; p.ntaps = 51; p.deemph = 1; p.dc_clip = 1;
         RC_API_CUDA(launch_epilogue(p, batch, st), "epilogue");
         std::swap(d_zi, d_zi_next);
@@ -294,6 +312,8 @@ struct rc_engine {
     struct Chan { long long roll, B, A; int mode; double tau; int bank, slot; };
     std::vector<Chan> chans;
     std::map<long long, FftPlan> planB;     // inverse channel FFT plans by bandwidth
+    std::map<long long, const float*> wtab; // Hann weights of the gathered bins by bandwidth (LoadTunerGather)
+    std::map<long long, float> wneg;
     struct Bank {
         DemodBank demod;
         const FftPlan* planB = nullptr;
@@ -358,7 +378,14 @@ int rc_engine_commit(rc_engine* e) {
     size_t maxB = 0;
     for (size_t i = 0; i < e->chans.size(); i++) {
         auto& c = e->chans[i];
-        if (!e->planB.count(c.B)) RC_API_CUDA(fft_plan_build(e->planB[c.B], c.B, e->store), "plan B");
+        if (!e->planB.count(c.B)) {
+            RC_API_CUDA(fft_plan_build(e->planB[c.B], c.B, e->store), "plan B");
+            float wn = 0.f;
+            float* d = nullptr;
+            RC_API_CUDA(e->arena.upload(&d, tuner_window_table(e->N, c.B, &wn)), "window table");
+            e->wtab[c.B] = d;
+            e->wneg[c.B] = wn;
+        }
         if ((size_t)c.B > maxB) maxB = (size_t)c.B;
         if (c.mode == RC_MODE_NONE) continue;
         int found = -1;
@@ -380,7 +407,7 @@ int rc_engine_commit(rc_engine* e) {
         if (rc) return rc;
         bk.planB = &e->planB[c0.B];
         std::vector<long long> rolls;
-        for (int m : bk.members) rolls.push_back(e->chans[m].roll);
+        for (int m : bk.members) rolls.push_back(((e->chans[m].roll % e->N) + e->N) % e->N);
         RC_API_CUDA(e->arena.upload(&bk.d_roll, rolls), "rolls");
         RC_API_CUDA(e->arena.alloc(&bk.y, (size_t)batch * c0.B), "alloc y");
         if (bk.planB->max_passes() >= 2) RC_API_CUDA(e->arena.alloc(&bk.w0, (size_t)batch * c0.B), "alloc yw0");
@@ -390,7 +417,7 @@ int rc_engine_commit(rc_engine* e) {
     }
     e->audio_total = off;
     std::vector<long long> all;
-    for (auto& c : e->chans) all.push_back(c.roll);
+    for (auto& c : e->chans) all.push_back(((c.roll % e->N) + e->N) % e->N);
     RC_API_CUDA(e->arena.upload(&e->d_roll_all, all), "rolls all");
     e->y_single_len = maxB;
     RC_API_CUDA(e->arena.alloc(&e->y_single, maxB * 2), "alloc y_single");
@@ -440,12 +467,11 @@ int rc_engine_load(rc_engine* e, const void* iq_dev, void* stream) {
     return RC_OK;
 }
 
-static LoadResampleGather tuner_gather(const rc_engine* e, const long long* d_roll, long long B) {
-    LoadResampleGather ld;
-    ld.X = e->X; ld.x_batch_stride = 0; ld.roll = d_roll;
-    ld.n_x = e->N; ld.num = B; ld.m = B < e->N ? B : e->N; ld.m2 = ld.m / 2 + 1;
-    ld.win = make_window(true, e->N);
-    ld.scale = (float)(1.0 / (double)e->N);     // resample scale B/N times the inverse FFT's 1/B
+static LoadTunerGather tuner_gather(const rc_engine* e, const long long* d_roll, long long B) {
+    LoadTunerGather ld;
+    ld.X = e->X; ld.roll = d_roll; ld.wtab = e->wtab.at(B);
+    ld.n_x = e->N; ld.num = B; ld.half = B / 2;
+    ld.w_neg_half = e->wneg.at(B);
     return ld;
 }
 
@@ -683,6 +709,7 @@ int rc_deemph_run(rc_deemph* d, const float* in, float* outp, void* stream) {
     DeviceGuard g(d->device);
     EpilogueParams p;
     p.in = in; p.out = outp; p.zi = d->d_zi; p.zi_next = d->d_zi_next; p.taps = d->d_taps;
+    p.stage = nullptr; p.partial = nullptr;
     p.A = d->size; p.nch = 1; p.ntaps = 51; p.deemph = 1; p.dc_clip = 0;
     RC_API_CUDA(launch_epilogue(p, 1, (cudaStream_t)stream), "deemph");
     std::swap(d->d_zi, d->d_zi_next);
@@ -730,7 +757,7 @@ int rc_bandpass_run(rc_bandpass* b, const float* in, float* outp, void* stream) 
     if (b->size <= 3 * (long long)b->taps.size())
         return fail(RC_ERR_INVALID, "The length of the input vector x must be greater than padlen");
     DeviceGuard g(b->device);
-    RC_API_CUDA(launch_ew(b->size, 1, FiltFiltEw{in, outp, b->d_g, b->size, b->K}, (cudaStream_t)stream), "filtfilt");
+    RC_API_CUDA(launch_filtfilt(FiltFiltEw{in, outp, b->d_g, b->size, b->K}, 1, (cudaStream_t)stream), "filtfilt");
     return RC_OK;
 }
 

@@ -1,21 +1,24 @@
-// rc_exec.cuh -- runs an FftPlan: picks the register-radix passes (rc_fft2.cuh)
+// rc_exec.cuh -- runs an FftPlan: picks the register-radix passes (rc_fft3.cuh)
 // when the plan has them and the fused load/store functors are ones those
 // kernels are instantiated for, the generic shared-memory passes otherwise.
 #pragma once
 
 #include "rc_ops.cuh"
+#include "rc_tma.cuh"
 
 namespace rc {
 
-// ---- the functor kinds the register-radix kernels are compiled for ----------
-enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2 };
+// ---- the functor kinds the register-radix kernels (rc_fft3.cuh) are compiled for ----
+enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2, kLdTma = 3 };
 enum { kStC64 = 0, kStLmr = 1 };
 
 struct LoadAny {
     int kind;
-    LoadC64 c64;
-    LoadResampleGather gather;
+    int box_rows;              // kLdTma: rows per TMA box
+    LoadC64 c64;               // kLdC64; also the source described by `tmap` (kLdTma)
+    LoadTunerGather gather;
     LoadDiscriminatorPacked disc;
+    CUtensorMap tmap;          // host copy; handed to the kernel as its own __grid_constant__ argument
 };
 struct StoreAny {
     int kind;
@@ -23,45 +26,62 @@ struct StoreAny {
     StoreLmrPacked lmr;
 };
 
-template <class L> struct V2LoadOk { static constexpr bool value = false; };
-template <> struct V2LoadOk<LoadC64> { static constexpr bool value = true; };
-template <> struct V2LoadOk<LoadResampleGather> { static constexpr bool value = true; };
-template <> struct V2LoadOk<LoadDiscriminatorPacked> { static constexpr bool value = true; };
-template <class S> struct V2StoreOk { static constexpr bool value = false; };
-template <> struct V2StoreOk<StoreC64> { static constexpr bool value = true; };
-template <> struct V2StoreOk<StoreLmrPacked> { static constexpr bool value = true; };
+template <class L> struct V3LoadOk { static constexpr bool value = false; };
+template <> struct V3LoadOk<LoadC64> { static constexpr bool value = true; };
+template <> struct V3LoadOk<LoadTunerGather> { static constexpr bool value = true; };
+template <> struct V3LoadOk<LoadDiscriminatorPacked> { static constexpr bool value = true; };
+template <class S> struct V3StoreOk { static constexpr bool value = false; };
+template <> struct V3StoreOk<StoreC64> { static constexpr bool value = true; };
+template <> struct V3StoreOk<StoreLmrPacked> { static constexpr bool value = true; };
 
-inline LoadAny to_any(const LoadC64& l) { LoadAny a{}; a.kind = kLdC64; a.c64 = l; return a; }
-inline LoadAny to_any(const LoadResampleGather& l) { LoadAny a{}; a.kind = kLdGather; a.gather = l; return a; }
-inline LoadAny to_any(const LoadDiscriminatorPacked& l) { LoadAny a{}; a.kind = kLdDisc; a.disc = l; return a; }
+// A complex64 source becomes a TMA tile load when its layout allows a tensor map.
+inline LoadAny to_any(const LoadC64& l, const FftPass& P, int batch) {
+    LoadAny a{};
+    a.kind = kLdC64;
+    a.c64 = l;
+#ifdef RC_EMULATE
+    (void)batch;
+    if (P.stride % 2 == 0 && l.batch_stride % 2 == 0) { a.kind = kLdTma; a.box_rows = tma_box_rows(P.R); }
+#else
+    static const bool no_tma = getenv("RC_NO_TMA") != nullptr;
+    TileSource src{l.p, P.stride, l.batch_stride, P.stride, P.R, batch};
+    if (!no_tma && tma_source_ok(src)) {
+        const int br = tma_box_rows(P.R);
+        if (tma_encode_tile_map(&a.tmap, src, br)) { a.kind = kLdTma; a.box_rows = br; }
+    }
+#endif
+    return a;
+}
+inline LoadAny to_any(const LoadTunerGather& l, const FftPass&, int) { LoadAny a{}; a.kind = kLdGather; a.gather = l; return a; }
+inline LoadAny to_any(const LoadDiscriminatorPacked& l, const FftPass&, int) { LoadAny a{}; a.kind = kLdDisc; a.disc = l; return a; }
 inline StoreAny to_any(const StoreC64& s) { StoreAny a{}; a.kind = kStC64; a.c64 = s; return a; }
 inline StoreAny to_any(const StoreLmrPacked& s) { StoreAny a{}; a.kind = kStLmr; a.lmr = s; return a; }
 
-// Defined in rc_fft2_g<k>.cu (schedule ids with id % kV2Groups == k).
-#define RC_V2_DECL(k)                                                                                         \
-    cudaError_t v2_first_g##k(int id, int sign, const FftPass& P, const LoadAny& ld, const StoreC64& st,      \
+// Defined in rc_fft3_g<k>.cu (schedule ids with id % kV3Groups == k).
+#define RC_V3_DECL(k)                                                                                         \
+    cudaError_t v3_first_g##k(int id, int sign, const FftPass& P, const LoadAny& ld, const StoreC64& st,      \
                               int batch, cudaStream_t stream);                                                \
-    cudaError_t v2_later_g##k(int id, int sign, const FftPass& P, const LoadC64& ld, const StoreAny& st,      \
+    cudaError_t v3_later_g##k(int id, int sign, const FftPass& P, const LoadAny& ld, const StoreAny& st,      \
                               int batch, cudaStream_t stream);
-RC_V2_DECL(0) RC_V2_DECL(1) RC_V2_DECL(2) RC_V2_DECL(3)
-#undef RC_V2_DECL
+RC_V3_DECL(0) RC_V3_DECL(1) RC_V3_DECL(2) RC_V3_DECL(3)
+#undef RC_V3_DECL
 
-inline cudaError_t v2_first(const FftPass& P, int sign, const LoadAny& ld, const StoreC64& st, int batch,
+inline cudaError_t v3_first(const FftPass& P, int sign, const LoadAny& ld, const StoreC64& st, int batch,
                             cudaStream_t stream) {
-    switch (P.fast_id % kV2Groups) {
-        case 0: return v2_first_g0(P.fast_id, sign, P, ld, st, batch, stream);
-        case 1: return v2_first_g1(P.fast_id, sign, P, ld, st, batch, stream);
-        case 2: return v2_first_g2(P.fast_id, sign, P, ld, st, batch, stream);
-        default: return v2_first_g3(P.fast_id, sign, P, ld, st, batch, stream);
+    switch (P.fast_id % kV3Groups) {
+        case 0: return v3_first_g0(P.fast_id, sign, P, ld, st, batch, stream);
+        case 1: return v3_first_g1(P.fast_id, sign, P, ld, st, batch, stream);
+        case 2: return v3_first_g2(P.fast_id, sign, P, ld, st, batch, stream);
+        default: return v3_first_g3(P.fast_id, sign, P, ld, st, batch, stream);
     }
 }
-inline cudaError_t v2_later(const FftPass& P, int sign, const LoadC64& ld, const StoreAny& st, int batch,
+inline cudaError_t v3_later(const FftPass& P, int sign, const LoadAny& ld, const StoreAny& st, int batch,
                             cudaStream_t stream) {
-    switch (P.fast_id % kV2Groups) {
-        case 0: return v2_later_g0(P.fast_id, sign, P, ld, st, batch, stream);
-        case 1: return v2_later_g1(P.fast_id, sign, P, ld, st, batch, stream);
-        case 2: return v2_later_g2(P.fast_id, sign, P, ld, st, batch, stream);
-        default: return v2_later_g3(P.fast_id, sign, P, ld, st, batch, stream);
+    switch (P.fast_id % kV3Groups) {
+        case 0: return v3_later_g0(P.fast_id, sign, P, ld, st, batch, stream);
+        case 1: return v3_later_g1(P.fast_id, sign, P, ld, st, batch, stream);
+        case 2: return v3_later_g2(P.fast_id, sign, P, ld, st, batch, stream);
+        default: return v3_later_g3(P.fast_id, sign, P, ld, st, batch, stream);
     }
 }
 
@@ -115,8 +135,8 @@ cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const Sto
                      float2* work0, float2* work1, cudaStream_t stream, const char* tag = "fft",
                      double in_bytes = 0.0, double out_bytes = 0.0) {
     if (batch <= 0) return cudaSuccess;
-    constexpr bool v2ok = V2LoadOk<LoadOp>::value && V2StoreOk<StoreOp>::value;
-    const bool fast = v2ok && plan.nfast >= 2;
+    constexpr bool v3ok = V3LoadOk<LoadOp>::value && V3StoreOk<StoreOp>::value;
+    const bool fast = v3ok && plan.nfast >= 2 && plan.n < (1LL << 31);
     const int npass = fast ? plan.nfast : plan.npass;
     const FftPass* passes = fast ? plan.fast : plan.pass;
     const double plain = 8.0 * (double)plan.n * (double)batch;
@@ -132,10 +152,10 @@ cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const Sto
         ProfileScope scope(name, ((first && in_bytes > 0) ? in_bytes : plain) + ((last && out_bytes > 0) ? out_bytes : plain), stream);
         cudaError_t e = cudaSuccess;
         if (fast) {
-            if constexpr (v2ok) {
-                if (first) e = v2_first(P, SIGN, to_any(ld), smid, batch, stream);
-                else if (last) e = v2_later(P, SIGN, lmid, to_any(st), batch, stream);
-                else e = v2_later(P, SIGN, lmid, to_any(smid), batch, stream);
+            if constexpr (v3ok) {
+                if (first) e = v3_first(P, SIGN, to_any(ld, P, batch), smid, batch, stream);
+                else if (last) e = v3_later(P, SIGN, to_any(lmid, P, batch), to_any(st), batch, stream);
+                else e = v3_later(P, SIGN, to_any(lmid, P, batch), to_any(smid), batch, stream);
             }
         } else if (first && last) e = fft_generic_pass<SIGN>(P, batch, ld, st, stream);
         else if (first) e = fft_generic_pass<SIGN>(P, batch, ld, smid, stream);

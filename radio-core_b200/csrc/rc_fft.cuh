@@ -49,12 +49,50 @@
 namespace rc {
 
 // ------------------------------------------------------------------ complex
-RC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-RC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-RC_HD float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// On sm_100a a float2 lives in an aligned register pair and FADD2 / FMUL2 / FFMA2
+// work on both halves at once, with per-half negate and half-swap operand
+// modifiers: a complex add is one instruction, a complex multiply two, and a
+// multiplication by +-i folds into the operand modifiers of its consumer.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(RC_NO_PACKED)
+#define RC_PACKED 1
+#endif
+RC_HD float2 cadd(float2 a, float2 b) {
+#ifdef RC_PACKED
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
 }
-RC_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+RC_HD float2 csub(float2 a, float2 b) {
+#ifdef RC_PACKED
+    return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+RC_HD float2 cmul(float2 a, float2 b) {
+#ifdef RC_PACKED
+    const float2 p = __fmul2_rn(a, make_float2(b.x, b.x));
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), p);
+#else
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
+}
+RC_HD float2 cscale(float2 a, float s) {
+#ifdef RC_PACKED
+    return __fmul2_rn(a, make_float2(s, s));
+#else
+    return make_float2(a.x * s, a.y * s);
+#endif
+}
+// a + s*b with a real scale (both halves)
+RC_HD float2 caxpy(float2 a, float s, float2 b) {
+#ifdef RC_PACKED
+    return __ffma2_rn(b, make_float2(s, s), a);
+#else
+    return make_float2(a.x + s * b.x, a.y + s * b.y);
+#endif
+}
 RC_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 RC_HD double2 cmul64(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -101,7 +139,7 @@ template <int SIGN> struct Dft<3, SIGN> {
         const float h = 0.86602540378443865f;   // sin(2 pi / 3)
         float2 t1 = cadd(v[1], v[2]);
         float2 t2 = csub(v[1], v[2]);
-        float2 m = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+        float2 m = caxpy(v[0], -0.5f, t1);
         float2 r = mul_si<SIGN>(cscale(t2, h));  // SIGN*i*h*(v1-v2)
         v[0] = cadd(v[0], t1);
         v[1] = cadd(m, r);
@@ -127,11 +165,11 @@ template <int SIGN> struct Dft<5, SIGN> {
         float2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
         float2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
         float2 x0 = v[0];
-        v[0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
-        float2 p1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
-        float2 p2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
-        float2 q1 = mul_si<SIGN>(make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y));
-        float2 q2 = mul_si<SIGN>(make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y));
+        v[0] = cadd(x0, cadd(a1, a2));
+        float2 p1 = caxpy(caxpy(x0, c1, a1), c2, a2);
+        float2 p2 = caxpy(caxpy(x0, c2, a1), c1, a2);
+        float2 q1 = mul_si<SIGN>(caxpy(cscale(b1, s1), s2, b2));
+        float2 q2 = mul_si<SIGN>(caxpy(cscale(b1, s2), -s1, b2));
         v[1] = cadd(p1, q1);
         v[4] = csub(p1, q1);
         v[2] = cadd(p2, q2);
@@ -232,7 +270,8 @@ struct FftPass {
     const int* pos;        // time index t -> shared-memory slot (digit reversal)
     int threads;
     int smem_elems;
-    int fast_id;           // >= 0: register-radix schedule of rc_fft2.cuh, -1: generic kernel
+    int fast_id;           // >= 0: register-radix schedule of rc_fft3.cuh, -1: generic kernel
+    int pair_ok;           // outputs of this pass may be written as aligned element pairs (rc_fft3.cuh)
 };
 
 RC_HD int fft_phys(const FftPass& P, int p, int c) {
@@ -247,17 +286,47 @@ RC_HD double2 fft_tw64(const FftPass& P, unsigned long long q) {
 }
 
 // ------------------------------------------------------------ generic I/O ops
+// 16-byte global accesses (two adjacent complex64); the caller guarantees alignment
+RC_HD float4 ldg4(const float2* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg((const float4*)p);
+#else
+    return make_float4(p[0].x, p[0].y, p[1].x, p[1].y);
+#endif
+}
+RC_HD void stg4(float2* p, float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    *(float4*)p = make_float4(a.x, a.y, b.x, b.y);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
 struct LoadC64 {          // contiguous complex64 batches
     const float2* p;
     long long batch_stride;
     RC_HD float2 operator()(int b, long long i) const { return ldg(p + b * batch_stride + i); }
+    // elements i and i+1 (the second only when has_b); 16-byte load when the address allows it
+    struct Ctx { const float2* base; };
+    RC_HD Ctx prepare(int b) const { return Ctx{p + b * batch_stride}; }
+    RC_HD float4 load2(const Ctx& c, long long i, bool has_b) const {
+        const float2* q = c.base + i;
+        if (has_b && (((size_t)q) & 15) == 0) return ldg4(q);
+        const float2 a = ldg(q);
+        const float2 d = has_b ? ldg(q + 1) : make_float2(0.f, 0.f);
+        return make_float4(a.x, a.y, d.x, d.y);
+    }
 };
 struct StoreC64 {
     float2* p;
     long long batch_stride;
     float scale;
     RC_HD void operator()(int b, long long i, float2 v) const {
-        p[b * batch_stride + i] = make_float2(v.x * scale, v.y * scale);
+        p[b * batch_stride + i] = cscale(v, scale);
+    }
+    // elements i and i+1, i even and the batch base 16-byte aligned (FftPass::pair_ok)
+    RC_HD void pair(int b, long long i, float2 v, float2 w) const {
+        stg4(p + b * batch_stride + i, cscale(v, scale), cscale(w, scale));
     }
 };
 
@@ -557,6 +626,7 @@ inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long lon
         P.tw_lo = (const double2*)store.put(key + ":lo", nullptr, 0, &err);
         P.tw_hi = (const double2*)store.put(key + ":hi", nullptr, 0, &err);
     }
+    P.pair_ok = (Ns == 1) ? (P.R % 2 == 0) : (Ns % 2 == 0);
     P.smem_elems = T > 1 ? P.R * (T + 1) : P.R + (P.R >> 4) + 1;
     long long work = (long long)P.R * T;
     int th = (int)((work / 8 + 31) / 32 * 32);
@@ -566,53 +636,102 @@ inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long lon
     return err;
 }
 
-// ---- register-radix schedules (rc_fft2.cuh): X(id, R0, R1, R2, threads, min CTAs/SM) ----
-// R = R0*R1*R2; R1 == 1 marks a two-stage schedule.  Kernels are instantiated in
-// rc_fft2_g*.cu, one group per translation unit (id % 4) so they compile in parallel.
-#define RC_V2_GROUP0(X) X(0, 10, 1, 10, 160, 4) X(4, 10, 1, 16, 128, 4) X(8, 4, 8, 10, 256, 2) X(12, 6, 10, 10, 320, 2) X(16, 8, 10, 10, 320, 2)
-#define RC_V2_GROUP1(X) X(1, 5, 5, 5, 400, 2) X(5, 10, 1, 20, 160, 4) X(9, 4, 10, 10, 320, 2) X(13, 5, 5, 25, 400, 1) X(17, 10, 10, 10, 400, 1)
-#define RC_V2_GROUP2(X) X(2, 8, 1, 16, 128, 4) X(6, 5, 5, 10, 400, 2) X(10, 5, 10, 10, 400, 2) X(14, 8, 8, 10, 256, 2)
-#define RC_V2_GROUP3(X) X(3, 10, 1, 15, 160, 4) X(7, 16, 1, 16, 256, 2) X(11, 8, 8, 8, 256, 2) X(15, 5, 6, 10, 160, 4)
-#define RC_V2_ALL(X) RC_V2_GROUP0(X) RC_V2_GROUP1(X) RC_V2_GROUP2(X) RC_V2_GROUP3(X)
-constexpr int kV2Groups = 4;
+// ---- register-radix schedules (rc_fft3.cuh): X(id, R0, R1, R2, threads, min CTAs/SM) ----
+// R = R0*R1*R2; R1 == 1 marks a two-stage schedule.  A thread owns two columns, so a
+// stage has (R / radix) * 8 butterfly pairs per tile and threads / 8 of them run at once.
+// Kernels are instantiated in rc_fft3_g*.cu, one group per translation unit (id % 4) so
+// they compile in parallel.
+#define RC_V3_GROUP0(X) X(20, 8, 1, 8, 64, 10) X(0, 10, 1, 10, 80, 10) X(4, 10, 1, 16, 128, 4) X(8, 5, 6, 10, 240, 3) X(12, 8, 8, 8, 256, 2) X(16, 8, 10, 10, 320, 2)
+#define RC_V3_GROUP1(X) X(21, 8, 1, 10, 80, 10) X(1, 8, 1, 16, 128, 4) X(5, 4, 5, 10, 200, 4) X(9, 4, 8, 10, 320, 2) X(13, 6, 10, 10, 160, 2) X(17, 10, 10, 10, 400, 1)
+#define RC_V3_GROUP2(X) X(18, 5, 1, 8, 64, 10) X(2, 5, 5, 5, 200, 4) X(6, 5, 5, 10, 200, 4) X(10, 5, 8, 10, 320, 2) X(14, 5, 5, 25, 200, 2)
+#define RC_V3_GROUP3(X) X(19, 5, 1, 10, 80, 10) X(3, 10, 1, 15, 128, 4) X(7, 4, 8, 8, 256, 4) X(11, 5, 10, 10, 200, 3) X(15, 8, 8, 10, 256, 2)
+#define RC_V3_ALL(X) RC_V3_GROUP0(X) RC_V3_GROUP1(X) RC_V3_GROUP2(X) RC_V3_GROUP3(X)
+constexpr int kV3Groups = 4;
 
-struct V2Entry { int id, R0, R1, R2, threads; int R() const { return R0 * R1 * R2; } };
-inline const std::vector<V2Entry>& v2_table() {
-    static const std::vector<V2Entry> t = {
-#define RC_V2_ROW(id, r0, r1, r2, nt, mb) {id, r0, r1, r2, nt},
-        RC_V2_ALL(RC_V2_ROW)
-#undef RC_V2_ROW
+struct V3Entry { int id, R0, R1, R2, threads; int R() const { return R0 * R1 * R2; } };
+inline const std::vector<V3Entry>& v3_table() {
+    static const std::vector<V3Entry> t = {
+#define RC_V3_ROW(id, r0, r1, r2, nt, mb) {id, r0, r1, r2, nt},
+        RC_V3_ALL(RC_V3_ROW)
+#undef RC_V3_ROW
     };
     return t;
 }
-inline const V2Entry* v2_find(int R) {
-    for (const V2Entry& e : v2_table()) if (e.R() == R) return &e;
+inline const V3Entry* v3_find(int R) {
+    for (const V3Entry& e : v3_table()) if (e.R() == R) return &e;
     return nullptr;
 }
 
-// Split n into 2..4 curated pass lengths; false when n has no such split.
+// Relative cost of one pass of length R (1.0 = a pass running at the best measured rate;
+// B200, 256 M-point transforms, tools/membench.cu + bench per-kernel timings): small tiles keep
+// many CTAs per SM and overlap their load / compute / store phases, long ones do not.
+inline double fft_pass_cost(int R, bool first) {
+    double c;
+    if (R <= 50) c = 1.25;            // tiny tiles: per-CTA fixed costs show
+    else if (R <= 160) c = 1.0;
+    else if (R <= 256) c = 1.05;
+    else if (R <= 400) c = 1.12;
+    else if (R <= 512) c = 1.18;
+    else if (R <= 640) c = 1.22;
+    else if (R <= 800) c = 1.20;
+    else c = 1.8;                     // one CTA per SM
+    if (R == 625) c += 0.1;           // radix-25 stage
+    if (first) c *= R > 512 ? 1.3 : 1.1;   // column runs re-ordered through registers + shared memory
+    return c;
+}
+
+// Split n into 2..4 curated pass lengths of least estimated cost; false when n has no such split.
+// RC_FFT_SPLIT="n:r0xr1x..;n:..." forces a split (kernel experiments).
 inline bool fft_choose_fast(long long n, std::vector<int>& Rs) {
     std::vector<int> cur;
-    for (const V2Entry& e : v2_table()) if (n % e.R() == 0) cur.push_back(e.R());
+    int max_r = 1 << 30;
+    if (const char* env = getenv("RC_FFT_MAXR")) max_r = atoi(env);      // experiments: cap the pass length
+    if (const char* env = getenv("RC_FFT_SPLIT")) {
+        std::string e(env);
+        size_t pos = 0;
+        while (pos < e.size()) {
+            size_t end = e.find(';', pos);
+            if (end == std::string::npos) end = e.size();
+            std::string item = e.substr(pos, end - pos);
+            pos = end + 1;
+            size_t colon = item.find(':');
+            if (colon == std::string::npos || atoll(item.substr(0, colon).c_str()) != n) continue;
+            std::vector<int> r;
+            long long prod = 1;
+            std::string rest = item.substr(colon + 1);
+            size_t q = 0;
+            while (q < rest.size()) {
+                size_t x = rest.find('x', q);
+                if (x == std::string::npos) x = rest.size();
+                int v = atoi(rest.substr(q, x - q).c_str());
+                if (v <= 0 || !v3_find(v)) { r.clear(); break; }
+                r.push_back(v);
+                prod *= v;
+                q = x + 1;
+            }
+            if (r.size() >= 2 && r.size() <= (size_t)kMaxPasses && prod == n) { Rs = r; return true; }
+        }
+    }
+    for (const V3Entry& e : v3_table()) if (n % e.R() == 0 && e.R() <= max_r) cur.push_back(e.R());
     double best = 1e30;
     std::vector<int> pick;
     auto score = [&](const std::vector<int>& r) {
-        double s = 1000.0 * r.size();
+        double s = 0.0;
         long long Ns = 1;
-        int maxR = 0;
         for (size_t i = 0; i < r.size(); i++) {
-            if ((n / r[i]) % 16) s += 10;              // input rows not 128-byte aligned
-            if (i > 0 && (Ns % 16)) s += 10;           // output tiles straddle Ns blocks
-            if (r[i] > maxR) maxR = r[i];
+            double c = fft_pass_cost(r[i], i == 0);
+            if ((n / r[i]) % 16) c += 0.05;            // input rows not 128-byte aligned
+            if (i > 0 && (Ns % 16)) c += 0.05;         // output tiles straddle Ns blocks
+            s += c;
             Ns *= r[i];
         }
-        return s + maxR / 100.0;
+        return s;
     };
     std::vector<int> r;
     std::function<void(long long, int)> rec = [&](long long rest, int depth) {
         if (rest == 1 && r.size() >= 2) {
             double sc = score(r);
-            if (sc < best) { best = sc; pick = r; }
+            if (sc < best - 1e-9) { best = sc; pick = r; }
             return;
         }
         if (depth == kMaxPasses) return;
@@ -647,7 +766,7 @@ inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store)
         plan.nfast = (int)Fs.size();
         Ns = 1;
         for (int i = 0; i < plan.nfast; i++) {
-            cudaError_t err = fft_fill_pass(plan.fast[i], n, Fs[i], 16, Ns, store, v2_find(Fs[i])->id);
+            cudaError_t err = fft_fill_pass(plan.fast[i], n, Fs[i], 16, Ns, store, v3_find(Fs[i])->id);
             if (err != cudaSuccess) return err;
             Ns *= Fs[i];
         }

@@ -80,15 +80,110 @@ struct LoadResampleGather {
 };
 
 // ---------------------------------------------------------------------------
+// LoadOp: Tuner.run's gather (tuner.py:151-161) for the engine's batched path:
+// even channel size num < n_x.  Same arithmetic as LoadResampleGather, but the
+// Hann weights W(kc)*scale are read from a table built once per channel size on
+// the host (fp64 cosine, rounded to fp32; all channels of a bank share it):
+//   i <= num/2 :  X[(i - r) mod n_x]            * wtab[i]      (kc = i)
+//   i >  num/2 :  X[(n_x - num + i - r) mod n_x] * wtab[i]      (kc = i - num)
+//   i == num/2 additionally + X[(n_x - num/2 - r) mod n_x] * w_neg_half   (merged +-num/2 bins)
+// roll r is normalised to [0, n_x) on the host.
+// ---------------------------------------------------------------------------
+struct LoadTunerGather {
+    const float2* X;           // spectrum, n_x bins
+    const long long* roll;     // per-batch roll in bins, in [0, n_x)
+    const float* wtab;         // num weights
+    long long n_x, num, half;
+    float w_neg_half;
+
+    RC_HD float2 one(long long r, long long i) const {
+        long long s = (i <= half ? i : i + (n_x - num)) - r;
+        if (s < 0) s += n_x;
+        float2 v = cscale(ldg(X + s), ldg(wtab + i));
+        if (i == half) {
+            long long s2 = n_x - half - r;
+            if (s2 < 0) s2 += n_x;
+            v = caxpy(v, w_neg_half, ldg(X + s2));
+        }
+        return v;
+    }
+    RC_HD float2 operator()(int b, long long i) const { return one(ldg(roll + b), i); }
+
+    // per-thread context of the register-radix kernels (n_x < 2^31: 32-bit index arithmetic)
+    struct Ctx { unsigned r, nx, gap, half; long long r64; };
+    RC_HD Ctx prepare(int b) const {
+        Ctx c;
+        c.r64 = ldg(roll + b);
+        c.r = (unsigned)c.r64; c.nx = (unsigned)n_x; c.gap = (unsigned)(n_x - num); c.half = (unsigned)half;
+        return c;
+    }
+    RC_HD float4 load2(const Ctx& c, long long i64, bool has_b) const {
+        if (n_x >= (1LL << 30)) {                                       // 3*n_x must fit 32 bits below
+            const float2 a = one(c.r64, i64);
+            const float2 d = has_b ? one(c.r64, i64 + 1) : make_float2(0.f, 0.f);
+            return make_float4(a.x, a.y, d.x, d.y);
+        }
+        const unsigned i = (unsigned)i64;
+        // s = src(i) - r (mod n_x), src(i) = i (i <= half) or i + gap
+        unsigned s = i + c.nx - c.r + (i > c.half ? c.gap : 0u);        // in [1, 3 n_x)
+        if (s >= c.nx) s -= c.nx;
+        if (s >= c.nx) s -= c.nx;
+        unsigned s1 = s + 1u + (i == c.half ? c.gap : 0u);
+        if (s1 >= c.nx) s1 -= c.nx;
+        float2 a = cscale(ldg(X + s), ldg(wtab + i));
+        float2 d = make_float2(0.f, 0.f);
+        if (has_b) d = cscale(ldg(X + s1), ldg(wtab + i + 1));
+        if (i == c.half || i + 1u == c.half) {                          // the merged +-num/2 bin
+            unsigned s2 = 2u * c.nx - c.half - c.r;
+            if (s2 >= c.nx) s2 -= c.nx;
+            if (s2 >= c.nx) s2 -= c.nx;
+            const float2 e = ldg(X + s2);
+            if (i == c.half) a = caxpy(a, w_neg_half, e);
+            else if (has_b) d = caxpy(d, w_neg_half, e);
+        }
+        return make_float4(a.x, a.y, d.x, d.y);
+    }
+};
+
+// ---------------------------------------------------------------------------
 // LoadOp: FM discriminator feeding a packed real FFT.
 // fm.py:60-65: angle -> unwrap -> diff -> pad(1,0) -> /pi, i.e.
 // d[0] = 0, d[n] = wrap(angle(y[n]) - angle(y[n-1]))/pi = angle(y[n]*conj(y[n-1]))/pi.
 // Element i of the half-length complex sequence is (d[2i], d[2i+1]).
 // ---------------------------------------------------------------------------
+RC_HD float2 f4lo_(float4 v) { return make_float2(v.x, v.y); }
+RC_HD float2 f4hi_(float4 v) { return make_float2(v.z, v.w); }
+// atan2(y, x) / pi, branch-free: octant reduction to t = min/max in [0, 1], then
+// atan(t)/(pi t) as a degree-7 polynomial in t^2 (minimax fit, max error 1.2e-8 in
+// units of pi before rounding; fp32 evaluation keeps it below 1e-7).
+RC_HD float atan2pi_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+#ifdef __CUDA_ARCH__
+    float t = __fdividef(mn, mx);
+#else
+    float t = mn / mx;
+#endif
+    if (!(mx > 0.f)) t = 0.f;
+    const float s = t * t;
+    float p = -0.0012906081974506378f;
+    p = fmaf(p, s, 0.006959192920476198f);
+    p = fmaf(p, s, -0.0177974421530962f);
+    p = fmaf(p, s, 0.03069206513464451f);
+    p = fmaf(p, s, -0.044272541999816895f);
+    p = fmaf(p, s, 0.06349188834428787f);
+    p = fmaf(p, s, -0.10609224438667297f);
+    p = fmaf(p, s, 0.3183096647262573f);
+    float r = t * p;
+    if (ay > ax) r = 0.5f - r;
+    if (x < 0.f) r = 1.0f - r;
+    return copysignf(r, y);
+}
+
 RC_HD float fm_step(float2 cur, float2 prev) {
     const float re = cur.x * prev.x + cur.y * prev.y;
     const float im = cur.y * prev.x - cur.x * prev.y;
-    return atan2f(im, re) * kInvPiF;
+    return atan2pi_fast(im, re);
 }
 
 struct LoadDiscriminatorPacked {
@@ -99,6 +194,26 @@ struct LoadDiscriminatorPacked {
         const float2 y0 = ldg(p), y1 = ldg(p + 1);
         const float d0 = (i == 0) ? 0.f : fm_step(y0, ldg(p - 1));
         return make_float2(d0, fm_step(y1, y0));
+    }
+    // packed elements i and i+1: d[2i .. 2i+3] from y[2i-1 .. 2i+3]
+    struct Ctx { const float2* base; };
+    RC_HD Ctx prepare(int b) const { return Ctx{y + b * batch_stride}; }
+    RC_HD float4 load2(const Ctx& c, long long i, bool has_b) const {
+        const float2* p = c.base + 2 * i;
+        float2 y0, y1, y2 = make_float2(1.f, 0.f), y3 = y2;
+        if ((((size_t)p) & 15) == 0) {
+            const float4 q = ldg4(p);
+            y0 = f4lo_(q); y1 = f4hi_(q);
+            if (has_b) { const float4 q2 = ldg4(p + 2); y2 = f4lo_(q2); y3 = f4hi_(q2); }
+        } else {
+            y0 = ldg(p); y1 = ldg(p + 1);
+            if (has_b) { y2 = ldg(p + 2); y3 = ldg(p + 3); }
+        }
+        const float d0 = (i == 0) ? 0.f : fm_step(y0, ldg(p - 1));
+        const float d1 = fm_step(y1, y0);
+        const float d2 = has_b ? fm_step(y2, y1) : 0.f;
+        const float d3 = has_b ? fm_step(y3, y2) : 0.f;
+        return make_float4(d0, d1, d2, d3);
     }
 };
 
@@ -234,6 +349,13 @@ struct StoreLmrPacked {
         const float2 m = *(const float2*)(mpx + o);
         *(float2*)(lmr + o) = make_float2(one(p.x, v.x, m.x), one(p.y, v.y, m.y));
     }
+    // packed elements i and i+1 (i even): four consecutive samples
+    RC_HD void pair(int b, long long i, float2 v, float2 w) const {
+        const long long o = b * n + 2 * i;
+        const float4 p = *(const float4*)(pilot + o);
+        const float4 m = *(const float4*)(mpx + o);
+        *(float4*)(lmr + o) = make_float4(one(p.x, v.x, m.x), one(p.y, v.y, m.y), one(p.z, w.x, m.z), one(p.w, w.y, m.w));
+    }
 };
 
 // StoreOp: analytic signal z[n] = p[n] + i*hhat[n] (PLL.step standalone).
@@ -352,6 +474,8 @@ struct EpilogueParams {
     float* out;           // [batch][A][nch]   interleaved, final
     double* zi;           // [batch][nch][K]   carried filter state (K = ntaps-1)
     double* zi_next;      // scratch of the same shape
+    double* stage;        // [batch][nch][A]   filtered audio before mean removal (dc_clip only)
+    double* partial;      // [batch][nch][chunks] per-chunk sums (dc_clip only)
     const float* taps;    // ntaps FIR taps (float32 values, as the reference stores them)
     long long A;
     int nch, ntaps;
@@ -390,53 +514,149 @@ RC_HD float epi_finish(const EpilogueParams& p, double v, double mean) {
     return (float)v;
 }
 
+// ---- shared FIR machinery of the epilogue and of the zero-phase filter ----------
+// A CTA of kFirThreads threads produces kFirChunk consecutive outputs of
+//   acc[n] = sum_{j < ntaps} taps[j] * xs[n + j]          (correlation form)
+// from a shared-memory window xs (fp64, converted once on load).  Each thread owns
+// 8 consecutive outputs and slides a 16-value register window over the taps, so
+// one shared-memory read feeds eight fp64 FMAs.
+constexpr int kFirThreads = 128;
+constexpr int kFirPer = 8;
+constexpr int kFirChunk = kFirThreads * kFirPer;     // outputs per CTA
+constexpr int kFirMaxTaps = 136;                     // padded tap count supported (multiple of 8)
+
 #if defined(__CUDACC__) && !defined(RC_EMULATE)
-constexpr int kEpiThreads = 1024;
-static __global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpilogueParams p) {
-    __shared__ double red[kEpiThreads];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const long long total = p.A * p.nch;
-    double sum = 0.0;
-    for (long long e = tid; e < total; e += kEpiThreads) {
-        const int ch = (int)(e % p.nch);
-        const long long n = e / p.nch;
-        const double v = epi_fir(p, b, ch, n);
-        sum += v;
-        p.out[(long long)b * total + e] = (float)v;      // staged; finished below by the same thread
+__device__ __forceinline__ void fir_window8(const double* xs, const double* taps, int ntaps8, int o, double acc[kFirPer]) {
+    double w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = xs[o + i];
+    for (int j0 = 0; j0 < ntaps8; j0 += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[8 + i] = xs[o + j0 + 8 + i];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            const double t = taps[j0 + jj];
+#pragma unroll
+            for (int r = 0; r < kFirPer; r++) acc[r] = fma(t, w[r + jj], acc[r]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = w[8 + i];
     }
-    red[tid] = sum;
+}
+
+// Phase 1 of the audio epilogue: de-emphasis FIR of one chunk, fp64 staging, per-chunk sum.
+static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const EpilogueParams p, int nchunks) {
+    __shared__ double xs[kFirChunk + kFirMaxTaps + 8];
+    __shared__ double tp[kFirMaxTaps];
+    __shared__ double red[kFirThreads / 32];
+    const int bc = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const int K = p.deemph ? p.ntaps - 1 : 0;
+    const int ntaps8 = p.deemph ? (p.ntaps + 7) / 8 * 8 : 8;
+    const long long n0 = (long long)chunk * kFirChunk;
+    const float* a = p.in + (long long)bc * p.A;
+    // xs[i] = x[n0 - K + i] (0 before the block: the carried state zi covers that part)
+    for (int i = tid; i < kFirChunk + ntaps8 + 8; i += kFirThreads) {
+        const long long idx = n0 - K + i;
+        xs[i] = (idx >= 0 && idx < p.A) ? (double)a[idx] : 0.0;
+    }
+    for (int i = tid; i < ntaps8; i += kFirThreads) {
+        double t = 0.0;
+        if (p.deemph) { if (i <= K) t = (double)p.taps[K - i]; }       // reversed taps: y[n] = sum_k b[k] x[n-k]
+        else if (i == 0) t = 1.0;
+        tp[i] = t;
+    }
     __syncthreads();
-    for (int s = kEpiThreads / 2; s > 0; s >>= 1) {
-        if (tid < s) red[tid] += red[tid + s];
-        __syncthreads();
-    }
-    const double mean = red[0] / (double)total;
-    if (p.deemph) {
-        const int K = p.ntaps - 1;
-        for (int e = tid; e < K * p.nch; e += kEpiThreads)
-            p.zi_next[(long long)b * p.nch * K + e] = epi_next_state(p, b, e / K, e % K);
+    double acc[kFirPer];
+#pragma unroll
+    for (int r = 0; r < kFirPer; r++) acc[r] = 0.0;
+    const int o = tid * kFirPer;
+    fir_window8(xs, tp, ntaps8, o, acc);
+    double sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < kFirPer; r++) {
+        const long long n = n0 + o + r;
+        if (n < p.A) {
+            double v = acc[r];
+            if (p.deemph && n < K) v += p.zi[(long long)bc * K + n];
+            sum += v;
+            if (p.dc_clip) p.stage[(long long)bc * p.A + n] = v;
+            else p.out[(long long)bc * p.A + n] = (float)v;             // nch == 1 without mean removal
+        }
     }
     if (p.dc_clip) {
-        for (long long e = tid; e < total; e += kEpiThreads) {
-            // re-evaluate in fp64 rather than re-reading the fp32 staging value
-            const double v = epi_fir(p, b, (int)(e % p.nch), e / p.nch);
-            p.out[(long long)b * total + e] = epi_finish(p, v, mean);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+        if ((tid & 31) == 0) red[tid >> 5] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kFirThreads / 32; w++) t += red[w];
+            p.partial[(long long)bc * nchunks + chunk] = t;
         }
+    }
+    if (p.deemph && chunk == nchunks - 1 && tid < K) {
+        const int b = bc / p.nch, ch = bc - b * p.nch;
+        p.zi_next[(long long)bc * K + tid] = epi_next_state(p, b, ch, tid);
+    }
+}
+
+// Phase 2: block mean over all nch*A samples of the channel, subtract, clip, interleave.
+static __global__ void __launch_bounds__(256) epi_finish_kernel(const EpilogueParams p, int nchunks) {
+    __shared__ double mean_s;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const long long total = p.A * p.nch;
+    if (tid < 32) {
+        double t = 0.0;
+        for (int i = tid; i < nchunks * p.nch; i += 32) t += p.partial[(long long)b * p.nch * nchunks + i];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+        if (tid == 0) mean_s = t / (double)total;
+    }
+    __syncthreads();
+    const double mean = mean_s;
+    for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(e % p.nch);
+        const long long n = e / p.nch;
+        p.out[(long long)b * total + e] = epi_finish(p, p.stage[((long long)b * p.nch + ch) * p.A + n], mean);
+    }
+}
+
+// Zero-phase FIR (FiltFiltEw) with shared-memory staging of the odd-extended input.
+static __global__ void __launch_bounds__(kFirThreads) filtfilt_kernel(const FiltFiltEw f) {
+    __shared__ double xs[kFirChunk + kFirMaxTaps + 8];
+    __shared__ double tp[kFirMaxTaps];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int ntaps = 2 * f.K + 1, ntaps8 = (ntaps + 7) / 8 * 8;
+    const long long n0 = (long long)blockIdx.x * kFirChunk;
+    const float* xb = f.x + (long long)b * f.n;
+    for (int i = tid; i < kFirChunk + ntaps8 + 8; i += kFirThreads) {
+        const long long idx = n0 - f.K + i;
+        xs[i] = (idx < f.n + f.K) ? f.xe(xb, idx) : 0.0;
+    }
+    for (int i = tid; i < ntaps8; i += kFirThreads) tp[i] = i < ntaps ? f.g[i] : 0.0;
+    __syncthreads();
+    double acc[kFirPer];
+#pragma unroll
+    for (int r = 0; r < kFirPer; r++) acc[r] = 0.0;
+    const int o = tid * kFirPer;
+    fir_window8(xs, tp, ntaps8, o, acc);
+#pragma unroll
+    for (int r = 0; r < kFirPer; r++) {
+        const long long n = n0 + o + r;
+        if (n < f.n) f.out[(long long)b * f.n + n] = (float)acc[r];
     }
 }
 #endif
 
+inline int epi_chunks(long long A) { return (int)((A + kFirChunk - 1) / kFirChunk); }
+
 inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStream_t stream) {
 #ifdef RC_EMULATE
-    const int nth = 1024;
     const long long total = p.A * p.nch;
     for (int b = 0; b < batch; b++) {
-        std::vector<double> red(nth, 0.0);
-        for (int tid = 0; tid < nth; tid++)
-            for (long long e = tid; e < total; e += nth) red[tid] += epi_fir(p, b, (int)(e % p.nch), e / p.nch);
-        for (int s = nth / 2; s > 0; s >>= 1)
-            for (int tid = 0; tid < s; tid++) red[tid] += red[tid + s];
-        const double mean = red[0] / (double)total;
+        double sum = 0.0;
+        for (long long e = 0; e < total; e++) sum += epi_fir(p, b, (int)(e % p.nch), e / p.nch);
+        const double mean = sum / (double)total;
         if (p.deemph) {
             const int K = p.ntaps - 1;
             for (int e = 0; e < K * p.nch; e++)
@@ -449,8 +669,32 @@ inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStrea
     return cudaSuccess;
 #else
     if (batch <= 0) return cudaSuccess;
-    ProfileScope scope("demod.epilogue", 8.0 * (double)p.A * p.nch * batch, stream);
-    epilogue_kernel<<<batch, kEpiThreads, 0, stream>>>(p);
+    if (p.ntaps > kFirMaxTaps - 8 || (!p.dc_clip && p.nch != 1)) return cudaErrorInvalidValue;
+    const int nchunks = epi_chunks(p.A);
+    {
+        ProfileScope scope("demod.deemph_fir", (4.0 + (p.dc_clip ? 8.0 : 4.0)) * (double)p.A * p.nch * batch, stream);
+        epi_fir_kernel<<<dim3((unsigned)nchunks, (unsigned)(batch * p.nch)), kFirThreads, 0, stream>>>(p, nchunks);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (p.dc_clip) {
+        ProfileScope scope("demod.mean_clip", 12.0 * (double)p.A * p.nch * batch, stream);
+        int gx = (int)((p.A * p.nch + 1023) / 1024);
+        if (gx < 1) gx = 1;
+        epi_finish_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, stream>>>(p, nchunks);
+    }
+    return cudaGetLastError();
+#endif
+}
+
+inline cudaError_t launch_filtfilt(const FiltFiltEw& f, int batch, cudaStream_t stream, const char* tag = "filtfilt") {
+#ifdef RC_EMULATE
+    return launch_ew(f.n, batch, f, stream);
+#else
+    if (batch <= 0 || f.n <= 0) return cudaSuccess;
+    if (2 * f.K + 1 > kFirMaxTaps - 8) return launch_ew(f.n, batch, f, stream, tag, 8.0 * (double)f.n * batch);
+    ProfileScope scope(tag, 8.0 * (double)f.n * batch, stream);
+    filtfilt_kernel<<<dim3((unsigned)((f.n + kFirChunk - 1) / kFirChunk), (unsigned)batch), kFirThreads, 0, stream>>>(f);
     return cudaGetLastError();
 #endif
 }

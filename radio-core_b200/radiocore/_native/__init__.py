@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libradiocore_b200.so")
+# RADIOCORE_B200_LIB: point at an alternative build of the same C ABI (kernel experiments)
+LIB_PATH = os.environ.get("RADIOCORE_B200_LIB") or os.path.join(_HERE, "libradiocore_b200.so")
 
 _lib = None
 

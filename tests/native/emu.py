@@ -253,3 +253,11 @@ class Tuner:
             a = self._audio[off.value: off.value + A.value * nch.value].reshape(A.value, nch.value).copy()
             res.append(a[None] if nch.value == 2 else a)
         return res
+
+
+def fft(x, sign=-1):
+    """rc_fft_c2c on the replay build: batched unnormalised FFT of a (batch, n) complex64 array."""
+    x = _c64(np.atleast_2d(x))
+    out = np.empty_like(x)
+    _check(lib().rc_fft_c2c(0, C.c_int64(x.shape[1]), x.shape[0], sign, _p(x), _p(out), None))
+    return out

@@ -1,0 +1,18 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+python __graft_entry__.py > gpurun_out/build.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+B="python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline"
+run() { name=$1; shift; env "$@" timeout 300 $B --workload cfg3 > gpurun_out/bench_cfg3_$name.json 2> gpurun_out/bench_cfg3_$name.err; }
+run default RC_X=1
+run s1 "RC_FFT_SPLIT=256000000:128x125x128x125;1000000:100x100x100;500000:100x100x50"
+run s2 "RC_FFT_SPLIT=256000000:400x800x800;1000000:100x100x100;500000:500x1000"
+run s3 "RC_FFT_SPLIT=256000000:640x640x625;1000000:125x80x100;500000:250x2000"
+run s4 "RC_FFT_SPLIT=256000000:500x640x800;1000000:250x4000;500000:125x80x50"
+run s5 "RC_FFT_SPLIT=256000000:160x160x100x100;1000000:200x50x100;500000:200x50x50"
+run s6 "RC_FFT_SPLIT=256000000:256x1000x1000;1000000:160x6250;500000:160x3125"
+timeout 300 $B --workload cfg2 --steps 20 > gpurun_out/bench_cfg2_v3.json 2> gpurun_out/bench_cfg2_v3.err
+timeout 300 $B --workload cfg4 --steps 20 > gpurun_out/bench_cfg4_v3.json 2> gpurun_out/bench_cfg4_v3.err
+du -sh gpurun_out
