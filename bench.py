@@ -279,21 +279,20 @@ def run_b200(args, rank, world, local_rank):
     nch = 2 if kind == "WBFM" else 1
     bcast = args.mode == "bcast" and world > 1
 
+    from radiocore.tools import sharding
+    tuner = radiocore.Tuner(cuda=True)
     if bcast:
-        # one wideband stream, replicated: rank 0 generates, NCCL broadcast per block,
+        # one wideband stream, replicated: rank 0 generates, one NCCL broadcast per block,
         # every rank demodulates its contiguous slice of the channels
-        my = list(range(rank * Cn // world, (rank + 1) * Cn // world))
         x_dev, offs = make_wideband_gpu(N, Cn, B, 3, kind == "WBFM", device)
+        my = sharding.shard_tuner(tuner, [100e6 + o for o in offs], B, lambda c: getattr(radiocore, kind)(B, A, cuda=True),
+                                  100e6, N, world, rank)
     else:
         my = list(range(Cn))
         x_dev, offs = make_wideband_gpu(N, Cn, B, 3 + rank, kind == "WBFM", device)
-
-    tuner = radiocore.Tuner(cuda=True)
-    for c in my:
-        tuner.add_channel(100e6 + offs[c], B, getattr(radiocore, kind)(B, A, cuda=True))
-    if bcast:                      # keep the band plan of the full stream
-        tuner._input_frequency = 100e6
-    tuner.request_bandwidth(N)
+        for c in my:
+            tuner.add_channel(100e6 + offs[c], B, getattr(radiocore, kind)(B, A, cuda=True))
+        tuner.request_bandwidth(N)
 
     def barrier():
         if world > 1:
@@ -302,7 +301,7 @@ def run_b200(args, rank, world, local_rank):
 
     def step_device():
         if bcast:
-            dist.broadcast(torch.view_as_real(x_dev), src=0)
+            sharding.broadcast_block(x_dev, src=0)
         tuner.load(x_dev)
         tuner.run_all()
 
@@ -332,29 +331,33 @@ def run_b200(args, rank, world, local_rank):
     lib.rc_profile_enable(0)
     lib.rc_profile_reset()
 
-    # ---- e2e: host IQ (pinned) -> public classes -> host audio for every channel
+    # ---- e2e: host IQ (pinned) -> public API -> host audio of every channel, every step.
+    # Tuner.submit()/collect() is the package's block pipeline: the H2D copy of block k+1 runs
+    # while block k is in the kernels and block k-1's audio is read back (depth 2).
     e2e = None
     if not args.no_e2e:
-        x_host = torch.empty(N, dtype=torch.complex64).pin_memory()
-        x_host.copy_(x_dev)
+        x_host = [torch.empty(N, dtype=torch.complex64).pin_memory() for _ in range(2)]
+        for xh in x_host:
+            xh.copy_(x_dev)
         torch.cuda.synchronize()
-        x_np = x_host.numpy()
-        chans = tuner.channels()
+        slices = tuner.audio_slices()
+        d2h = 4 * sum(size * nchn for _, size, nchn in slices)
 
-        def step_e2e():
-            tuner.load(x_np)
-            tot = 0
-            for ch in chans:
-                audio = ch.demodulator.run(tuner.run(ch.index))
-                tot += audio.nbytes
-            return tot
+        def run_e2e(steps):
+            prev, checksum = None, 0.0
+            for i in range(steps):
+                t = tuner.submit(x_host[i % 2])
+                if prev is not None:
+                    audio = tuner.collect(prev)
+                    checksum += float(audio[0])
+                prev = t
+            audio = tuner.collect(prev)
+            return checksum + float(audio[0])
 
-        d2h = step_e2e()
-        step_e2e()
+        run_e2e(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
+        run_e2e(args.steps)
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
         e2e = {"t": t_e2e, "h2d": 8 * N, "d2h": d2h}
@@ -419,7 +422,8 @@ def run_b200(args, rank, world, local_rank):
     if e2e:
         line["e2e"] = {"value": samples_per_step * args.steps / t_e2e / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                       "ms_per_step": t_e2e / args.steps * 1e3, "timing": "wall clock between device synchronisations, max over ranks"}
+                       "ms_per_step": t_e2e / args.steps * 1e3, "timing": "wall clock between device synchronisations, max over ranks",
+                       "api": "Tuner.submit()/collect(): pinned host IQ -> H2D -> kernels -> D2H of all channels' audio, 2 blocks in flight"}
     if world == 1 and not args.no_cpu_baseline:
         try:
             workers = host_workers(N, limit=None)

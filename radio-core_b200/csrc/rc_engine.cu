@@ -254,8 +254,26 @@ struct DemodBank {
 
     // y: [batch][B] complex64;  out: [batch][A][nch] float32
     int run(const float2* y, float* out, cudaStream_t st) {
-        RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadDiscriminatorPacked{y, B}, StoreC64{Z1, h, 1.0f}, w0, w1, st,
-                              "demod.rfft_disc", 8.0 * B * batch, 0.0)), "fft discriminator");
+        return run_from(LoadDiscriminatorPacked{y, B}, 8.0 * B * batch, out, st);
+    }
+    // ang: [batch][B] angle(y)/pi as stored by the engine's channel IFFT (StoreAngle)
+    int run_angle(const float* ang, float* out, cudaStream_t st) {
+        return run_from(LoadAnglePacked{ang, B}, 4.0 * B * batch, out, st);
+    }
+
+    template <class DiscLoad>
+    int run_from(const DiscLoad& disc, double disc_bytes, float* out, cudaStream_t st) {
+        if (mode != RC_MODE_WBFM) {
+            // Decimate keeps bins k < m2 of the discriminator's spectrum; through the packed-real
+            // algebra they depend on Z1[k] and Z1[h-k] only: skip the stores in between.
+            long long lo = (specBA.m2 + 2) / 2 * 2, hi = (h - specBA.m2 - 1) / 2 * 2;
+            if (hi < lo) hi = lo;
+            RC_API_CUDA((fft_exec<-1>(planBh, batch, disc, StoreC64Win{Z1, h, lo, hi}, w0, w1, st,
+                                  "demod.rfft_disc", disc_bytes, 8.0 * (double)(h - (hi - lo)) * batch)), "fft discriminator");
+        } else {
+            RC_API_CUDA((fft_exec<-1>(planBh, batch, disc, StoreC64{Z1, h, 1.0f}, w0, w1, st,
+                                  "demod.rfft_disc", disc_bytes, 0.0)), "fft discriminator");
+        }
         if (mode != RC_MODE_WBFM) {
             RC_API_CUDA(launch_ew(hp, batch, SpecResampleEw{specBA, Z1, ZpA}, st, "demod.spec_resample",
                                   24.0 * hp * batch), "spec B->A");
@@ -319,7 +337,8 @@ struct rc_engine {
         const FftPlan* planB = nullptr;
         std::vector<int> members;
         long long* d_roll = nullptr;
-        float2 *y = nullptr, *w0 = nullptr, *w1 = nullptr;
+        float* ang = nullptr;                   // angle(y)/pi of every channel sample (StoreAngle)
+        float2 *w0 = nullptr, *w1 = nullptr;
         long long audio_offset = 0;
     };
     std::vector<std::unique_ptr<Bank>> banks;
@@ -409,7 +428,7 @@ int rc_engine_commit(rc_engine* e) {
         std::vector<long long> rolls;
         for (int m : bk.members) rolls.push_back(((e->chans[m].roll % e->N) + e->N) % e->N);
         RC_API_CUDA(e->arena.upload(&bk.d_roll, rolls), "rolls");
-        RC_API_CUDA(e->arena.alloc(&bk.y, (size_t)batch * c0.B), "alloc y");
+        RC_API_CUDA(e->arena.alloc(&bk.ang, (size_t)batch * c0.B), "alloc angle");
         if (bk.planB->max_passes() >= 2) RC_API_CUDA(e->arena.alloc(&bk.w0, (size_t)batch * c0.B), "alloc yw0");
         if (bk.planB->max_passes() >= 3) RC_API_CUDA(e->arena.alloc(&bk.w1, (size_t)batch * c0.B), "alloc yw1");
         bk.audio_offset = off;
@@ -485,9 +504,10 @@ int rc_engine_run(rc_engine* e, float* audio_dev, void* stream) {
         auto& bk = *bp;
         const long long B = bk.demod.B;
         const int batch = bk.demod.batch;
-        RC_API_CUDA((fft_exec<+1>(*bk.planB, batch, tuner_gather(e, bk.d_roll, B), StoreC64{bk.y, B, 1.0f},
-                                  bk.w0, bk.w1, st, "tuner.channel_ifft")), "tuner channel ifft");
-        int rc = bk.demod.run(bk.y, audio_dev + bk.audio_offset, st);
+        RC_API_CUDA((fft_exec<+1>(*bk.planB, batch, tuner_gather(e, bk.d_roll, B), StoreAngle{bk.ang, B},
+                                  bk.w0, bk.w1, st, "tuner.channel_ifft", 12.0 * B * batch, 4.0 * B * batch)),
+                    "tuner channel ifft");
+        int rc = bk.demod.run_angle(bk.ang, audio_dev + bk.audio_offset, st);
         if (rc) return rc;
     }
     return RC_OK;

@@ -9,8 +9,8 @@
 namespace rc {
 
 // ---- the functor kinds the register-radix kernels (rc_fft3.cuh) are compiled for ----
-enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2, kLdTma = 3 };
-enum { kStC64 = 0, kStLmr = 1 };
+enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2, kLdTma = 3, kLdAng = 4 };
+enum { kStC64 = 0, kStLmr = 1, kStWin = 2, kStAng = 3 };
 
 struct LoadAny {
     int kind;
@@ -18,21 +18,27 @@ struct LoadAny {
     LoadC64 c64;               // kLdC64; also the source described by `tmap` (kLdTma)
     LoadTunerGather gather;
     LoadDiscriminatorPacked disc;
+    LoadAnglePacked angle;
     CUtensorMap tmap;          // host copy; handed to the kernel as its own __grid_constant__ argument
 };
 struct StoreAny {
     int kind;
     StoreC64 c64;
     StoreLmrPacked lmr;
+    StoreC64Win win;
+    StoreAngle angle;
 };
 
 template <class L> struct V3LoadOk { static constexpr bool value = false; };
 template <> struct V3LoadOk<LoadC64> { static constexpr bool value = true; };
 template <> struct V3LoadOk<LoadTunerGather> { static constexpr bool value = true; };
 template <> struct V3LoadOk<LoadDiscriminatorPacked> { static constexpr bool value = true; };
+template <> struct V3LoadOk<LoadAnglePacked> { static constexpr bool value = true; };
 template <class S> struct V3StoreOk { static constexpr bool value = false; };
 template <> struct V3StoreOk<StoreC64> { static constexpr bool value = true; };
 template <> struct V3StoreOk<StoreLmrPacked> { static constexpr bool value = true; };
+template <> struct V3StoreOk<StoreC64Win> { static constexpr bool value = true; };
+template <> struct V3StoreOk<StoreAngle> { static constexpr bool value = true; };
 
 // A complex64 source becomes a TMA tile load when its layout allows a tensor map.
 inline LoadAny to_any(const LoadC64& l, const FftPass& P, int batch) {
@@ -47,7 +53,7 @@ inline LoadAny to_any(const LoadC64& l, const FftPass& P, int batch) {
     TileSource src{l.p, P.stride, l.batch_stride, P.stride, P.R, batch};
     if (!no_tma && tma_source_ok(src)) {
         const int br = tma_box_rows(P.R);
-        if (tma_encode_tile_map(&a.tmap, src, br)) { a.kind = kLdTma; a.box_rows = br; }
+        if (tma_encode_tile_map(&a.tmap, src, br, P.T)) { a.kind = kLdTma; a.box_rows = br; }
     }
 #endif
     return a;
@@ -56,6 +62,9 @@ inline LoadAny to_any(const LoadTunerGather& l, const FftPass&, int) { LoadAny a
 inline LoadAny to_any(const LoadDiscriminatorPacked& l, const FftPass&, int) { LoadAny a{}; a.kind = kLdDisc; a.disc = l; return a; }
 inline StoreAny to_any(const StoreC64& s) { StoreAny a{}; a.kind = kStC64; a.c64 = s; return a; }
 inline StoreAny to_any(const StoreLmrPacked& s) { StoreAny a{}; a.kind = kStLmr; a.lmr = s; return a; }
+inline LoadAny to_any(const LoadAnglePacked& l, const FftPass&, int) { LoadAny a{}; a.kind = kLdAng; a.angle = l; return a; }
+inline StoreAny to_any(const StoreAngle& s) { StoreAny a{}; a.kind = kStAng; a.angle = s; return a; }
+inline StoreAny to_any(const StoreC64Win& s) { StoreAny a{}; a.kind = kStWin; a.win = s; return a; }
 
 // Defined in rc_fft3_g<k>.cu (schedule ids with id % kV3Groups == k).
 #define RC_V3_DECL(k)                                                                                         \

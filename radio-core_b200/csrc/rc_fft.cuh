@@ -330,6 +330,21 @@ struct StoreC64 {
     }
 };
 
+// complex64 store that keeps only the elements outside [lo, hi) of each batch entry: the
+// half-length spectrum of a real signal that is about to be truncated to its lowest bins
+// (Decimate, decimate.py:48) is only ever read near both ends.  lo and hi are even.
+struct StoreC64Win {
+    float2* p;
+    long long batch_stride;
+    long long lo, hi;
+    RC_HD void operator()(int b, long long i, float2 v) const {
+        if (i < lo || i >= hi) p[b * batch_stride + i] = v;
+    }
+    RC_HD void pair(int b, long long i, float2 v, float2 w) const {
+        if (i < lo || i >= hi) stg4(p + b * batch_stride + i, v, w);
+    }
+};
+
 // ------------------------------------------------------------- pass phases
 template <class LoadOp, int SIGN>
 RC_HD void fft_pass_load(float2* sm, const FftPass& P, const LoadOp& ld, int batch,
@@ -637,21 +652,21 @@ inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long lon
 }
 
 // ---- register-radix schedules (rc_fft3.cuh): X(id, R0, R1, R2, threads, min CTAs/SM) ----
-// R = R0*R1*R2; R1 == 1 marks a two-stage schedule.  A thread owns two columns, so a
+// (..., column pairs per tile).  R = R0*R1*R2; R1 == 1 marks a two-stage schedule.  A thread owns two columns, so a
 // stage has (R / radix) * 8 butterfly pairs per tile and threads / 8 of them run at once.
 // Kernels are instantiated in rc_fft3_g*.cu, one group per translation unit (id % 4) so
 // they compile in parallel.
-#define RC_V3_GROUP0(X) X(20, 8, 1, 8, 64, 10) X(0, 10, 1, 10, 80, 10) X(4, 10, 1, 16, 128, 4) X(8, 5, 6, 10, 240, 3) X(12, 8, 8, 8, 256, 2) X(16, 8, 10, 10, 320, 2)
-#define RC_V3_GROUP1(X) X(21, 8, 1, 10, 80, 10) X(1, 8, 1, 16, 128, 4) X(5, 4, 5, 10, 200, 4) X(9, 4, 8, 10, 320, 2) X(13, 6, 10, 10, 160, 2) X(17, 10, 10, 10, 400, 1)
-#define RC_V3_GROUP2(X) X(18, 5, 1, 8, 64, 10) X(2, 5, 5, 5, 200, 4) X(6, 5, 5, 10, 200, 4) X(10, 5, 8, 10, 320, 2) X(14, 5, 5, 25, 200, 2)
-#define RC_V3_GROUP3(X) X(19, 5, 1, 10, 80, 10) X(3, 10, 1, 15, 128, 4) X(7, 4, 8, 8, 256, 4) X(11, 5, 10, 10, 200, 3) X(15, 8, 8, 10, 256, 2)
+#define RC_V3_GROUP0(X) X(20, 8, 1, 8, 128, 8, 16) X(0, 10, 1, 10, 160, 6, 16) X(4, 10, 1, 16, 256, 3, 16) X(8, 5, 6, 10, 240, 3, 8) X(12, 8, 8, 8, 256, 2, 8) X(16, 8, 10, 10, 320, 2, 8)
+#define RC_V3_GROUP1(X) X(21, 8, 1, 10, 160, 6, 16) X(1, 8, 1, 16, 256, 3, 16) X(5, 4, 5, 10, 400, 2, 16) X(9, 4, 8, 10, 320, 2, 8) X(13, 6, 10, 10, 160, 2, 8) X(17, 10, 10, 10, 400, 1, 8)
+#define RC_V3_GROUP2(X) X(18, 5, 1, 8, 128, 8, 16) X(2, 5, 5, 5, 400, 2, 16) X(6, 5, 5, 10, 400, 2, 16) X(10, 5, 8, 10, 320, 2, 8) X(14, 5, 5, 25, 200, 2, 8)
+#define RC_V3_GROUP3(X) X(19, 5, 1, 10, 160, 6, 16) X(3, 10, 1, 15, 256, 3, 16) X(7, 4, 8, 8, 256, 4, 8) X(11, 5, 10, 10, 200, 3, 8) X(15, 8, 8, 10, 256, 2, 8)
 #define RC_V3_ALL(X) RC_V3_GROUP0(X) RC_V3_GROUP1(X) RC_V3_GROUP2(X) RC_V3_GROUP3(X)
 constexpr int kV3Groups = 4;
 
-struct V3Entry { int id, R0, R1, R2, threads; int R() const { return R0 * R1 * R2; } };
+struct V3Entry { int id, R0, R1, R2, threads, cp; int R() const { return R0 * R1 * R2; } };
 inline const std::vector<V3Entry>& v3_table() {
     static const std::vector<V3Entry> t = {
-#define RC_V3_ROW(id, r0, r1, r2, nt, mb) {id, r0, r1, r2, nt},
+#define RC_V3_ROW(id, r0, r1, r2, nt, mb, cp) {id, r0, r1, r2, nt, cp},
         RC_V3_ALL(RC_V3_ROW)
 #undef RC_V3_ROW
     };
@@ -667,17 +682,38 @@ inline const V3Entry* v3_find(int R) {
 // many CTAs per SM and overlap their load / compute / store phases, long ones do not.
 inline double fft_pass_cost(int R, bool first) {
     double c;
-    if (R <= 50) c = 1.25;            // tiny tiles: per-CTA fixed costs show
-    else if (R <= 160) c = 1.0;
-    else if (R <= 256) c = 1.05;
-    else if (R <= 400) c = 1.12;
-    else if (R <= 512) c = 1.18;
-    else if (R <= 640) c = 1.22;
-    else if (R <= 800) c = 1.20;
-    else c = 1.8;                     // one CTA per SM
-    if (R == 625) c += 0.1;           // radix-25 stage
-    if (first) c *= R > 512 ? 1.3 : 1.1;   // column runs re-ordered through registers + shared memory
+    if (R <= 50) c = 1.33;            // tiny tiles: per-CTA fixed costs show
+    else if (R <= 80) c = 1.12;
+    else if (R <= 100) c = 1.0;
+    else if (R <= 125) c = 1.06;
+    else if (R <= 160) c = 0.93;
+    else if (R <= 256) c = 1.0;
+    else if (R <= 400) c = 1.1;
+    else if (R <= 512) c = 1.08;
+    else if (R <= 640) c = 1.05;
+    else if (R <= 800) c = 1.08;
+    else c = 1.65;                    // one CTA per SM
+    if (R == 625) c += 0.15;          // radix-25 stage
+    if (first) c *= R > 640 ? 1.5 : 1.05;   // column runs re-ordered through registers + shared memory
     return c;
+}
+
+// Splits measured best on B200 for the sizes of the BASELINE configurations (bench.py per-kernel
+// timings, profiles/); everything else goes through the cost model.
+inline bool fft_tuned_split(long long n, std::vector<int>& Rs) {
+    struct Row { long long n; int r[4]; };
+    static const Row rows[] = {
+        {256000000LL, {640, 640, 625, 0}},
+        {1000000LL, {200, 50, 100, 0}},
+        {500000LL, {200, 50, 50, 0}},
+    };
+    for (const Row& row : rows)
+        if (row.n == n) {
+            Rs.clear();
+            for (int i = 0; i < 4 && row.r[i]; i++) Rs.push_back(row.r[i]);
+            return true;
+        }
+    return false;
 }
 
 // Split n into 2..4 curated pass lengths of least estimated cost; false when n has no such split.
@@ -712,6 +748,7 @@ inline bool fft_choose_fast(long long n, std::vector<int>& Rs) {
             if (r.size() >= 2 && r.size() <= (size_t)kMaxPasses && prod == n) { Rs = r; return true; }
         }
     }
+    if (max_r == (1 << 30) && fft_tuned_split(n, Rs)) return true;
     for (const V3Entry& e : v3_table()) if (n % e.R() == 0 && e.R() <= max_r) cur.push_back(e.R());
     double best = 1e30;
     std::vector<int> pick;
@@ -766,7 +803,7 @@ inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store)
         plan.nfast = (int)Fs.size();
         Ns = 1;
         for (int i = 0; i < plan.nfast; i++) {
-            cudaError_t err = fft_fill_pass(plan.fast[i], n, Fs[i], 16, Ns, store, v3_find(Fs[i])->id);
+            cudaError_t err = fft_fill_pass(plan.fast[i], n, Fs[i], 2 * v3_find(Fs[i])->cp, Ns, store, v3_find(Fs[i])->id);
             if (err != cudaSuccess) return err;
             Ns *= Fs[i];
         }

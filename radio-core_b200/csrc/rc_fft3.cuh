@@ -31,25 +31,26 @@
 
 namespace rc {
 
-constexpr int kV3T = 16;     // columns per tile
-constexpr int kV3CP = 8;     // column pairs per tile
-
-template <int R0_, int R1_, int R2_, int NT_, int MINB_>
+// CP = column pairs per tile: 8 (16 columns, 128-byte rows) or, for short passes whose tiles
+// stay small, 16 (32 columns, 256-byte rows: a whole DRAM segment per row).
+template <int R0_, int R1_, int R2_, int NT_, int MINB_, int CP_ = 8>
 struct V3Sched {
     static constexpr int R0 = R0_, R1 = R1_, R2 = R2_, NT = NT_, MINB = MINB_;
+    static constexpr int CP = CP_, T = 2 * CP_, LOGCP = CP_ == 8 ? 3 : 4;
     static constexpr int R = R0_ * R1_ * R2_;
     static constexpr int U = R1_ * R2_;
-    static constexpr int NG = NT_ / kV3CP;                   // row groups working in parallel
+    static constexpr int NG = NT_ / CP_;                     // row groups working in parallel
     static constexpr int NB0 = U, NB1 = R0_ * R2_, NB2 = R0_ * R1_;   // butterflies (per column pair) of each stage
     static constexpr int IT0 = (NB0 + NG - 1) / NG, IT1 = (NB1 + NG - 1) / NG, IT2 = (NB2 + NG - 1) / NG;
     static constexpr int HOLD = IT2 * R2_;                   // float4 registers held across the re-order (first pass)
     static constexpr int MINB_F_ = 65536 / (NT_ * (HOLD * 4 + 48));
     static constexpr int MINB_FIRST = MINB_F_ < 1 ? 1 : (MINB_F_ < MINB_ ? MINB_F_ : MINB_);
     static constexpr int PITCH = (R % 2 == 0) ? R + 1 : R;   // float2 pitch of the transposed [column][K] layout (odd)
-    static constexpr int TILE_F4 = R * kV3CP + 16;           // float4 slots: tile, and room for the transposed layout
+    static constexpr int TILE_F4 = R * CP_ + 2 * CP_;        // float4 slots: tile, and room for the transposed layout
     static constexpr int SMEM_BYTES = TILE_F4 * 16 + R * 8 + 16;   // + W_R table + mbarrier
-    static_assert(NT_ % kV3CP == 0, "threads must be a multiple of the column pairs");
-    static_assert(16 * PITCH <= TILE_F4 * 2, "transposed layout must fit the tile buffer");
+    static_assert(CP_ == 8 || CP_ == 16, "8 or 16 column pairs");
+    static_assert(NT_ % CP_ == 0, "threads must be a multiple of the column pairs");
+    static_assert(T * PITCH <= TILE_F4 * 2, "transposed layout must fit the tile buffer");
 };
 
 RC_HD float2 f4lo(float4 v) { return make_float2(v.x, v.y); }
@@ -67,11 +68,11 @@ RC_HD void v3_load_table(float2* tw, const FftPass& P, int tid) {
 }
 
 // Sources of stage 0: the tile already staged in shared memory (TMA), or a LoadOp functor.
-struct V3FromTile {
+template <int CP> struct V3FromTile {
     const float4* tile;
     struct Ctx {};
     RC_HD Ctx prepare(int) const { return Ctx{}; }
-    RC_HD float4 get(const Ctx&, int row, int cp, long long, bool) const { return tile[row * kV3CP + cp]; }
+    RC_HD float4 get(const Ctx&, int row, int cp, long long, bool) const { return tile[row * CP + cp]; }
 };
 template <class LoadOp> struct V3FromOp {
     const LoadOp* ld;
@@ -98,7 +99,7 @@ RC_HD V3Tw v3_twiddle_setup(const FftPass& P, long long j0, int tid) {
     V3Tw t;
     t.wa = t.wb = t.sta = t.stb = t.wsa = t.wsb = make_double2(1.0, 0.0);
     if (LATER) {
-        const int cp = tid & (kV3CP - 1), g = tid >> 3;
+        const int cp = tid & (S::CP - 1), g = tid >> S::LOGCP;
         const unsigned long long ns = (unsigned long long)P.Ns;
         const unsigned long long ka = (unsigned long long)(j0 + 2 * cp) % ns;
         const unsigned long long kb = (ka + 1 == ns) ? 0 : ka + 1;
@@ -118,7 +119,7 @@ RC_HD V3Tw v3_twiddle_setup(const FftPass& P, long long j0, int tid) {
 template <class S, int SIGN, bool LATER, class Src>
 RC_HD void v3_stage0(float4* tile, const float2* tw, const FftPass& P, const Src& src, int batch, long long j0, int tid,
                      const V3Tw& tws) {
-    const int cp = tid & (kV3CP - 1), g = tid >> 3;
+    const int cp = tid & (S::CP - 1), g = tid >> S::LOGCP;
     const long long j = j0 + 2 * cp;
     const bool act_a = j < P.stride, act_b = j + 1 < P.stride;
     double2 wa = tws.wa, wb = tws.wb;
@@ -163,14 +164,14 @@ RC_HD void v3_stage0(float4* tile, const float2* tw, const FftPass& P, const Src
             }
         }
 #pragma unroll
-        for (int k0 = 0; k0 < S::R0; k0++) tile[(k0 * S::U + u) * kV3CP + cp] = f4make(a[k0], b[k0]);
+        for (int k0 = 0; k0 < S::R0; k0++) tile[(k0 * S::U + u) * S::CP + cp] = f4make(a[k0], b[k0]);
     }
 }
 
 // middle stage (three-stage schedules only): radix R1 over digit d1, in place
 template <class S, int SIGN>
 RC_HD void v3_stage1(float4* tile, const float2* tw, int tid) {
-    const int cp = tid & (kV3CP - 1), g = tid >> 3;
+    const int cp = tid & (S::CP - 1), g = tid >> S::LOGCP;
 #pragma unroll
     for (int it = 0; it < S::IT1; it++) {
         const int q = g + it * S::NG;
@@ -180,7 +181,7 @@ RC_HD void v3_stage1(float4* tile, const float2* tw, int tid) {
         float2 a[S::R1], b[S::R1];
 #pragma unroll
         for (int t1 = 0; t1 < S::R1; t1++) {
-            const float4 x = tile[(base + t1 * S::R2) * kV3CP + cp];
+            const float4 x = tile[(base + t1 * S::R2) * S::CP + cp];
             a[t1] = f4lo(x);
             b[t1] = f4hi(x);
         }
@@ -198,14 +199,14 @@ RC_HD void v3_stage1(float4* tile, const float2* tw, int tid) {
             }
         }
 #pragma unroll
-        for (int k1 = 0; k1 < S::R1; k1++) tile[(base + k1 * S::R2) * kV3CP + cp] = f4make(a[k1], b[k1]);
+        for (int k1 = 0; k1 < S::R1; k1++) tile[(base + k1 * S::R2) * S::CP + cp] = f4make(a[k1], b[k1]);
     }
 }
 
 // last stage, passes after the first: radix R2 over digit d2, results straight to global
 template <class S, int SIGN, class StoreOp>
 RC_HD void v3_last_direct(const float4* tile, const FftPass& P, const StoreOp& st, int batch, long long j0, int tid) {
-    const int cp = tid & (kV3CP - 1), g = tid >> 3;
+    const int cp = tid & (S::CP - 1), g = tid >> S::LOGCP;
     const long long j = j0 + 2 * cp;
     if (j >= P.stride) return;
     const bool act_b = j + 1 < P.stride;
@@ -223,7 +224,7 @@ RC_HD void v3_last_direct(const float4* tile, const FftPass& P, const StoreOp& s
         float2 a[S::R2], b[S::R2];
 #pragma unroll
         for (int t2 = 0; t2 < S::R2; t2++) {
-            const float4 x = tile[(base + t2) * kV3CP + cp];
+            const float4 x = tile[(base + t2) * S::CP + cp];
             a[t2] = f4lo(x);
             b[t2] = f4hi(x);
         }
@@ -247,7 +248,7 @@ RC_HD void v3_last_direct(const float4* tile, const FftPass& P, const StoreOp& s
 // last stage of the first pass, part A: read + radix into held registers
 template <class S, int SIGN>
 RC_HD void v3_last_first_a(const float4* tile, float4* hold, int tid) {
-    const int cp = tid & (kV3CP - 1), g = tid >> 3;
+    const int cp = tid & (S::CP - 1), g = tid >> S::LOGCP;
 #pragma unroll
     for (int it = 0; it < S::IT2; it++) {
         const int q = g + it * S::NG;
@@ -257,7 +258,7 @@ RC_HD void v3_last_first_a(const float4* tile, float4* hold, int tid) {
         float2 a[S::R2], b[S::R2];
 #pragma unroll
         for (int t2 = 0; t2 < S::R2; t2++) {
-            const float4 x = tile[(base + t2) * kV3CP + cp];
+            const float4 x = tile[(base + t2) * S::CP + cp];
             a[t2] = f4lo(x);
             b[t2] = f4hi(x);
         }
@@ -270,7 +271,7 @@ RC_HD void v3_last_first_a(const float4* tile, float4* hold, int tid) {
 // part B (after a barrier): write the held results transposed, [column][K] with an odd pitch
 template <class S>
 RC_HD void v3_last_first_b(float2* tr, const float4* hold, int tid) {
-    const int cp = tid & (kV3CP - 1), g = tid >> 3;
+    const int cp = tid & (S::CP - 1), g = tid >> S::LOGCP;
 #pragma unroll
     for (int it = 0; it < S::IT2; it++) {
         const int q = g + it * S::NG;
@@ -291,13 +292,13 @@ template <class S, class StoreOp>
 RC_HD void v3_first_copy_out(const float2* tr, const FftPass& P, const StoreOp& st, int batch, long long j0, int tid) {
     if (S::R % 2 == 0 && P.pair_ok) {
         constexpr int H = S::R / 2;
-        for (int idx = tid; idx < H * kV3T; idx += S::NT) {
+        for (int idx = tid; idx < H * S::T; idx += S::NT) {
             const int c = idx / H, K = 2 * (idx - c * H);
             const long long j = j0 + c;
             if (j < P.stride) st.pair(batch, j * S::R + K, tr[c * S::PITCH + K], tr[c * S::PITCH + K + 1]);
         }
     } else {
-        for (int idx = tid; idx < S::R * kV3T; idx += S::NT) {
+        for (int idx = tid; idx < S::R * S::T; idx += S::NT) {
             const int c = idx / S::R, K = idx - c * S::R;
             const long long j = j0 + c;
             if (j < P.stride) st(batch, j * S::R + K, tr[c * S::PITCH + K]);

@@ -14,9 +14,9 @@ template <class S>
 __device__ __forceinline__ void v3_issue_tile(float4* tile, uint64_t* bar, const CUtensorMap* map, int box_rows,
                                               long long j0, int batch) {
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, (uint32_t)(S::R * kV3T * sizeof(float2)));
+    mbar_expect_tx(bar, (uint32_t)(S::R * S::T * sizeof(float2)));
     for (int r = 0; r < S::R; r += box_rows)
-        tma_load_3d(tile + (size_t)r * kV3CP, map, bar, (int)(j0 * 2), r, batch);
+        tma_load_3d(tile + (size_t)r * S::CP, map, bar, (int)(j0 * 2), r, batch);
 }
 
 // first pass of a plan: fused LoadOp (or TMA-staged complex64), column runs re-ordered through shared memory
@@ -28,7 +28,7 @@ v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __gr
     float2* tw = (float2*)(rc_v3_smem + (size_t)S::TILE_F4 * 16);
     uint64_t* bar = (uint64_t*)(tw + S::R);
     const int batch = blockIdx.y + blockIdx.z * gridDim.y;
-    const long long j0 = (long long)blockIdx.x * kV3T;
+    const long long j0 = (long long)blockIdx.x * S::T;
     if (j0 >= P.stride) return;                    // padding CTA of the last cluster
     const int tid = threadIdx.x;
     const bool tma = ld.kind == kLdTma;
@@ -39,10 +39,11 @@ v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __gr
     switch (ld.kind) {
         case kLdTma:
             mbar_wait(bar, 0);
-            v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTile{tile}, batch, j0, tid, tws);
+            v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTile<S::CP>{tile}, batch, j0, tid, tws);
             break;
         case kLdGather: v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadTunerGather>{&ld.gather, P.stride}, batch, j0, tid, tws); break;
         case kLdDisc: v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadDiscriminatorPacked>{&ld.disc, P.stride}, batch, j0, tid, tws); break;
+        case kLdAng: v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadAnglePacked>{&ld.angle, P.stride}, batch, j0, tid, tws); break;
         default: v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadC64>{&ld.c64, P.stride}, batch, j0, tid, tws); break;
     }
     __syncthreads();
@@ -68,7 +69,7 @@ v3_later_kernel(const FftPass P, const LoadAny ld, const StoreAny st, const __gr
     float2* tw = (float2*)(rc_v3_smem + (size_t)S::TILE_F4 * 16);
     uint64_t* bar = (uint64_t*)(tw + S::R);
     const int batch = blockIdx.y + blockIdx.z * gridDim.y;
-    const long long j0 = (long long)blockIdx.x * kV3T;
+    const long long j0 = (long long)blockIdx.x * S::T;
     if (j0 >= P.stride) return;
     const int tid = threadIdx.x;
     const bool tma = ld.kind == kLdTma;
@@ -78,7 +79,7 @@ v3_later_kernel(const FftPass P, const LoadAny ld, const StoreAny st, const __gr
     __syncthreads();
     if (tma) {
         mbar_wait(bar, 0);
-        v3_stage0<S, SIGN, true>(tile, tw, P, V3FromTile{tile}, batch, j0, tid, tws);
+        v3_stage0<S, SIGN, true>(tile, tw, P, V3FromTile<S::CP>{tile}, batch, j0, tid, tws);
     } else {
         v3_stage0<S, SIGN, true>(tile, tw, P, V3FromOp<LoadC64>{&ld.c64, P.stride}, batch, j0, tid, tws);
     }
@@ -88,6 +89,8 @@ v3_later_kernel(const FftPass P, const LoadAny ld, const StoreAny st, const __gr
         __syncthreads();
     }
     if (st.kind == kStLmr) v3_last_direct<S, SIGN>(tile, P, st.lmr, batch, j0, tid);
+    else if (st.kind == kStWin) v3_last_direct<S, SIGN>(tile, P, st.win, batch, j0, tid);
+    else if (st.kind == kStAng) v3_last_direct<S, SIGN>(tile, P, st.angle, batch, j0, tid);
     else v3_last_direct<S, SIGN>(tile, P, st.c64, batch, j0, tid);
 }
 
@@ -116,16 +119,16 @@ template <class S>
 void v3_emulate_tma(float4* tile, const LoadC64& src, const FftPass& P, int batch, long long j0) {
     float2* t = (float2*)tile;
     for (int r = 0; r < S::R; r++)
-        for (int c = 0; c < kV3T; c++) {
+        for (int c = 0; c < S::T; c++) {
             const long long j = j0 + c;
-            t[r * kV3T + c] = j < P.stride ? src(batch, j + (long long)r * P.stride) : make_float2(0.f, 0.f);
+            t[r * S::T + c] = j < P.stride ? src(batch, j + (long long)r * P.stride) : make_float2(0.f, 0.f);
         }
 }
 #endif
 
 template <class S, int SIGN>
 cudaError_t v3_run_first(const FftPass& P, const LoadAny& ld, const StoreC64& st, int batch, cudaStream_t stream) {
-    const long long tiles = (P.stride + kV3T - 1) / kV3T;
+    const long long tiles = (P.stride + S::T - 1) / S::T;
 #ifdef RC_EMULATE
     (void)stream;
     std::vector<float4> smv((size_t)S::SMEM_BYTES / 16 + 1), hold((size_t)S::NT * S::HOLD);
@@ -134,13 +137,14 @@ cudaError_t v3_run_first(const FftPass& P, const LoadAny& ld, const StoreC64& st
     for (int tid = 0; tid < S::NT; tid++) v3_load_table<S, SIGN>(tw, P, tid);
     for (int b = 0; b < batch; b++)
         for (long long t = 0; t < tiles; t++) {
-            const long long j0 = t * kV3T;
+            const long long j0 = t * S::T;
             if (ld.kind == kLdTma) v3_emulate_tma<S>(tile, ld.c64, P, b, j0);
             for (int tid = 0; tid < S::NT; tid++) {
                 const V3Tw tws = v3_twiddle_setup<S, false>(P, j0, tid);
-                if (ld.kind == kLdTma) v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTile{tile}, b, j0, tid, tws);
+                if (ld.kind == kLdTma) v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTile<S::CP>{tile}, b, j0, tid, tws);
                 else if (ld.kind == kLdGather) v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadTunerGather>{&ld.gather, P.stride}, b, j0, tid, tws);
                 else if (ld.kind == kLdDisc) v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadDiscriminatorPacked>{&ld.disc, P.stride}, b, j0, tid, tws);
+                else if (ld.kind == kLdAng) v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadAnglePacked>{&ld.angle, P.stride}, b, j0, tid, tws);
                 else v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadC64>{&ld.c64, P.stride}, b, j0, tid, tws);
             }
             if constexpr (S::R1 > 1) for (int tid = 0; tid < S::NT; tid++) v3_stage1<S, SIGN>(tile, tw, tid);
@@ -164,7 +168,7 @@ cudaError_t v3_run_first(const FftPass& P, const LoadAny& ld, const StoreC64& st
 
 template <class S, int SIGN>
 cudaError_t v3_run_later(const FftPass& P, const LoadAny& ld, const StoreAny& st, int batch, cudaStream_t stream) {
-    const long long tiles = (P.stride + kV3T - 1) / kV3T;
+    const long long tiles = (P.stride + S::T - 1) / S::T;
 #ifdef RC_EMULATE
     (void)stream;
     std::vector<float4> smv((size_t)S::SMEM_BYTES / 16 + 1);
@@ -173,16 +177,18 @@ cudaError_t v3_run_later(const FftPass& P, const LoadAny& ld, const StoreAny& st
     for (int tid = 0; tid < S::NT; tid++) v3_load_table<S, SIGN>(tw, P, tid);
     for (int b = 0; b < batch; b++)
         for (long long t = 0; t < tiles; t++) {
-            const long long j0 = t * kV3T;
+            const long long j0 = t * S::T;
             if (ld.kind == kLdTma) v3_emulate_tma<S>(tile, ld.c64, P, b, j0);
             for (int tid = 0; tid < S::NT; tid++) {
                 const V3Tw tws = v3_twiddle_setup<S, true>(P, j0, tid);
-                if (ld.kind == kLdTma) v3_stage0<S, SIGN, true>(tile, tw, P, V3FromTile{tile}, b, j0, tid, tws);
+                if (ld.kind == kLdTma) v3_stage0<S, SIGN, true>(tile, tw, P, V3FromTile<S::CP>{tile}, b, j0, tid, tws);
                 else v3_stage0<S, SIGN, true>(tile, tw, P, V3FromOp<LoadC64>{&ld.c64, P.stride}, b, j0, tid, tws);
             }
             if constexpr (S::R1 > 1) for (int tid = 0; tid < S::NT; tid++) v3_stage1<S, SIGN>(tile, tw, tid);
             for (int tid = 0; tid < S::NT; tid++) {
                 if (st.kind == kStLmr) v3_last_direct<S, SIGN>(tile, P, st.lmr, b, j0, tid);
+                else if (st.kind == kStWin) v3_last_direct<S, SIGN>(tile, P, st.win, b, j0, tid);
+                else if (st.kind == kStAng) v3_last_direct<S, SIGN>(tile, P, st.angle, b, j0, tid);
                 else v3_last_direct<S, SIGN>(tile, P, st.c64, b, j0, tid);
             }
         }
@@ -200,12 +206,12 @@ cudaError_t v3_run_later(const FftPass& P, const LoadAny& ld, const StoreAny& st
 #endif
 }
 
-#define RC_V3_CASE_FIRST(id, r0, r1, r2, nt, mb)                                                              \
-    case id: return sign < 0 ? v3_run_first<V3Sched<r0, r1, r2, nt, mb>, -1>(P, ld, st, batch, stream)        \
-                             : v3_run_first<V3Sched<r0, r1, r2, nt, mb>, +1>(P, ld, st, batch, stream);
-#define RC_V3_CASE_LATER(id, r0, r1, r2, nt, mb)                                                              \
-    case id: return sign < 0 ? v3_run_later<V3Sched<r0, r1, r2, nt, mb>, -1>(P, ld, st, batch, stream)        \
-                             : v3_run_later<V3Sched<r0, r1, r2, nt, mb>, +1>(P, ld, st, batch, stream);
+#define RC_V3_CASE_FIRST(id, r0, r1, r2, nt, mb, cp)                                                          \
+    case id: return sign < 0 ? v3_run_first<V3Sched<r0, r1, r2, nt, mb, cp>, -1>(P, ld, st, batch, stream)    \
+                             : v3_run_first<V3Sched<r0, r1, r2, nt, mb, cp>, +1>(P, ld, st, batch, stream);
+#define RC_V3_CASE_LATER(id, r0, r1, r2, nt, mb, cp)                                                          \
+    case id: return sign < 0 ? v3_run_later<V3Sched<r0, r1, r2, nt, mb, cp>, -1>(P, ld, st, batch, stream)    \
+                             : v3_run_later<V3Sched<r0, r1, r2, nt, mb, cp>, +1>(P, ld, st, batch, stream);
 
 #define RC_V3_DEFINE_GROUP(k, LIST)                                                                           \
     cudaError_t v3_first_g##k(int id, int sign, const FftPass& P, const LoadAny& ld, const StoreC64& st,      \

@@ -217,6 +217,62 @@ struct LoadDiscriminatorPacked {
     }
 };
 
+// ---------------------------------------------------------------------------
+// The same discriminator split at the phase, for the engine's batched path: the
+// last pass of the channel IFFT stores angle(y[n])/pi (4 bytes per sample instead
+// of the 8-byte IQ sample), the first pass of the packed real FFT takes wrapped
+// differences.  fm.py:60-65: d[0] = 0, d[n] = wrap(angle(y[n]) - angle(y[n-1]))/pi.
+// ---------------------------------------------------------------------------
+struct StoreAngle {
+    float* ang;                // [batch][n] angle / pi in (-1, 1]
+    long long batch_stride;
+    RC_HD void operator()(int b, long long i, float2 v) const { ang[b * batch_stride + i] = atan2pi_fast(v.y, v.x); }
+    RC_HD void pair(int b, long long i, float2 v, float2 w) const {
+        *(float2*)(ang + b * batch_stride + i) = make_float2(atan2pi_fast(v.y, v.x), atan2pi_fast(w.y, w.x));
+    }
+};
+
+RC_HD float wrap_half_turns(float x) {          // x in (-2, 2) half-turns -> (-1, 1]
+#ifdef __CUDA_ARCH__
+    return x - 2.0f * rintf(0.5f * x);
+#else
+    return x - 2.0f * nearbyintf(0.5f * x);
+#endif
+}
+
+struct LoadAnglePacked {
+    const float* ang;
+    long long batch_stride;
+    RC_HD float2 operator()(int b, long long i) const {
+        const float* p = ang + b * batch_stride + 2 * i;
+        const float a0 = ldg(p), a1 = ldg(p + 1);
+        const float d0 = (i == 0) ? 0.f : wrap_half_turns(a0 - ldg(p - 1));
+        return make_float2(d0, wrap_half_turns(a1 - a0));
+    }
+    struct Ctx { const float* base; };
+    RC_HD Ctx prepare(int b) const { return Ctx{ang + b * batch_stride}; }
+    RC_HD float4 load2(const Ctx& c, long long i, bool has_b) const {
+        const float* p = c.base + 2 * i;
+        float a0, a1, a2 = 0.f, a3 = 0.f;
+        if (has_b && (((size_t)p) & 15) == 0) {
+#ifdef __CUDA_ARCH__
+            const float4 q = __ldg((const float4*)p);
+#else
+            const float4 q = make_float4(p[0], p[1], p[2], p[3]);
+#endif
+            a0 = q.x; a1 = q.y; a2 = q.z; a3 = q.w;
+        } else {
+            a0 = ldg(p); a1 = ldg(p + 1);
+            if (has_b) { a2 = ldg(p + 2); a3 = ldg(p + 3); }
+        }
+        const float d0 = (i == 0) ? 0.f : wrap_half_turns(a0 - ldg(p - 1));
+        const float d1 = wrap_half_turns(a1 - a0);
+        const float d2 = has_b ? wrap_half_turns(a2 - a1) : 0.f;
+        const float d3 = has_b ? wrap_half_turns(a3 - a2) : 0.f;
+        return make_float4(d0, d1, d2, d3);
+    }
+};
+
 // Elementwise variant (used for odd sizes and by tests): d[b][n].
 struct DiscriminatorEw {
     const float2* y;
@@ -525,14 +581,21 @@ constexpr int kFirPer = 8;
 constexpr int kFirChunk = kFirThreads * kFirPer;     // outputs per CTA
 constexpr int kFirMaxTaps = 136;                     // padded tap count supported (multiple of 8)
 
+// window slot of logical sample i: one pad slot every 8 samples, so that threads reading
+// 8-sample groups 64 bytes apart land on different banks
+RC_HD int fir_slot(int i) { return i + (i >> 3); }
+constexpr int kFirSlots = kFirChunk + kFirMaxTaps + 8 + (kFirChunk + kFirMaxTaps + 8) / 8 + 1;
+
 #if defined(__CUDACC__) && !defined(RC_EMULATE)
 __device__ __forceinline__ void fir_window8(const double* xs, const double* taps, int ntaps8, int o, double acc[kFirPer]) {
     double w[16];
+    const double* x0 = xs + fir_slot(o);           // o is a multiple of 8: groups are contiguous
 #pragma unroll
-    for (int i = 0; i < 8; i++) w[i] = xs[o + i];
+    for (int i = 0; i < 8; i++) w[i] = x0[i];
     for (int j0 = 0; j0 < ntaps8; j0 += 8) {
+        const double* x1 = xs + fir_slot(o + j0 + 8);
 #pragma unroll
-        for (int i = 0; i < 8; i++) w[8 + i] = xs[o + j0 + 8 + i];
+        for (int i = 0; i < 8; i++) w[8 + i] = x1[i];
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
             const double t = taps[j0 + jj];
@@ -546,7 +609,7 @@ __device__ __forceinline__ void fir_window8(const double* xs, const double* taps
 
 // Phase 1 of the audio epilogue: de-emphasis FIR of one chunk, fp64 staging, per-chunk sum.
 static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const EpilogueParams p, int nchunks) {
-    __shared__ double xs[kFirChunk + kFirMaxTaps + 8];
+    __shared__ double xs[kFirSlots];
     __shared__ double tp[kFirMaxTaps];
     __shared__ double red[kFirThreads / 32];
     const int bc = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
@@ -557,7 +620,7 @@ static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const Epilo
     // xs[i] = x[n0 - K + i] (0 before the block: the carried state zi covers that part)
     for (int i = tid; i < kFirChunk + ntaps8 + 8; i += kFirThreads) {
         const long long idx = n0 - K + i;
-        xs[i] = (idx >= 0 && idx < p.A) ? (double)a[idx] : 0.0;
+        xs[fir_slot(i)] = (idx >= 0 && idx < p.A) ? (double)a[idx] : 0.0;
     }
     for (int i = tid; i < ntaps8; i += kFirThreads) {
         double t = 0.0;
@@ -623,7 +686,7 @@ static __global__ void __launch_bounds__(256) epi_finish_kernel(const EpiloguePa
 
 // Zero-phase FIR (FiltFiltEw) with shared-memory staging of the odd-extended input.
 static __global__ void __launch_bounds__(kFirThreads) filtfilt_kernel(const FiltFiltEw f) {
-    __shared__ double xs[kFirChunk + kFirMaxTaps + 8];
+    __shared__ double xs[kFirSlots];
     __shared__ double tp[kFirMaxTaps];
     const int b = blockIdx.y, tid = threadIdx.x;
     const int ntaps = 2 * f.K + 1, ntaps8 = (ntaps + 7) / 8 * 8;
@@ -631,7 +694,7 @@ static __global__ void __launch_bounds__(kFirThreads) filtfilt_kernel(const Filt
     const float* xb = f.x + (long long)b * f.n;
     for (int i = tid; i < kFirChunk + ntaps8 + 8; i += kFirThreads) {
         const long long idx = n0 - f.K + i;
-        xs[i] = (idx < f.n + f.K) ? f.xe(xb, idx) : 0.0;
+        xs[fir_slot(i)] = (idx < f.n + f.K) ? f.xe(xb, idx) : 0.0;
     }
     for (int i = tid; i < ntaps8; i += kFirThreads) tp[i] = i < ntaps ? f.g[i] : 0.0;
     __syncthreads();

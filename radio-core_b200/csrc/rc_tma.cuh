@@ -54,11 +54,11 @@ inline bool tma_source_ok(const TileSource& s) {
 }
 
 // rank-3 map over float32 pairs: dim0 = 2*cols floats (contiguous), dim1 = rows, dim2 = batch;
-// box = {32 floats (16 complex columns), box_rows, 1}.  Columns past `cols` read as zero.
-inline bool tma_encode_tile_map(CUtensorMap* map, const TileSource& s, int box_rows) {
+// box = {2*tile_cols floats, box_rows, 1}.  Columns past `cols` read as zero.
+inline bool tma_encode_tile_map(CUtensorMap* map, const TileSource& s, int box_rows, int tile_cols) {
     cuuint64_t dims[3] = {(cuuint64_t)s.cols * 2, (cuuint64_t)s.rows, (cuuint64_t)(s.batch > 0 ? s.batch : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)s.row_stride * 8, (cuuint64_t)(s.batch_stride > 0 ? s.batch_stride : s.row_stride * s.rows) * 8};
-    cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t box[3] = {(cuuint32_t)(2 * tile_cols), (cuuint32_t)box_rows, 1u};
     cuuint32_t es[3] = {1u, 1u, 1u};
     CUresult r = tma_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)s.base, dims, strides, box, es,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -4,5 +4,6 @@ from radiocore.tools.buffer import Buffer
 from radiocore.tools.ringbuffer import RingBuffer
 from radiocore.tools.carrousel import Carrousel
 from radiocore.tools.chopper import Chopper
+from radiocore.tools import sharding
 
-__all__ = ["Tuner", "Channel", "Buffer", "RingBuffer", "Carrousel", "Chopper"]
+__all__ = ["Tuner", "Channel", "Buffer", "RingBuffer", "Carrousel", "Chopper", "sharding"]

@@ -55,6 +55,7 @@ class Tuner:
         self._audio_serial = -1
         self._host_serial = -1
         self._input_ref = None
+        self._pipe = None          # block pipeline state of submit()/collect()
 
     # ------------------------------------------------------------ band plan
     @property
@@ -105,6 +106,12 @@ class Tuner:
     def _drop_engine(self):
         h, self._engine = self._engine, None
         self._engine_key = None
+        if self._pipe is not None:
+            self._pipe = None
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
         if h is not None:
             try:
                 _native.lib().rc_engine_destroy(h)
@@ -161,6 +168,8 @@ class Tuner:
         self._ensure_engine()
         if len(input_signal) != int(self._input_bandwidth):
             raise ValueError("input_signal size and input_bandwidth mismatch")
+        if self._pipe is not None:                   # blocks queued by submit() share the engine's scratch
+            self._pipe["compute"].synchronize()
         x = _device.to_device(input_signal, torch.complex64)
         self._input_ref = x
         _native.check(_native.lib().rc_engine_load(self._engine, x.data_ptr(), _device.stream_ptr()))
@@ -184,6 +193,73 @@ class Tuner:
             return self._audio_dev
         self._fetch_host()
         return self._audio_host.numpy()
+
+    # ------------------------------------------------- pipelined block interface
+    # The reference's loop (examples/multi_fm_server.py:95-106) is synchronous: get a block,
+    # load, demodulate, send.  A one-second block is 8 bytes per sample of host->device copy,
+    # which at PCIe rates takes longer than the kernels; submit()/collect() keep `depth` blocks
+    # in flight so the copy of block k+1 overlaps the kernels of block k and the read-back of
+    # block k-1.  Same arithmetic, same carried de-emphasis state, blocks processed in order.
+    def submit(self, input_signal, depth: int = 2):
+        """Queue one block (pinned host array or CUDA tensor); returns a ticket for collect()."""
+        self._ensure_engine()
+        n = int(self._input_bandwidth)
+        if len(input_signal) != n:
+            raise ValueError("input_signal size and input_bandwidth mismatch")
+        if self._pipe is None or self._pipe["depth"] != depth or self._pipe["engine"] is not self._engine:
+            total = max(self._audio_dev.numel(), 1)
+            self._pipe = {
+                "depth": depth, "engine": self._engine, "next": 0,
+                "copy": torch.cuda.Stream(), "compute": torch.cuda.Stream(), "out": torch.cuda.Stream(),
+                "x": [torch.empty(n, dtype=torch.complex64, device="cuda") for _ in range(depth)],
+                "audio": [torch.empty(total, dtype=torch.float32, device="cuda") for _ in range(depth)],
+                "host": [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(depth)],
+                "ev_in": [torch.cuda.Event() for _ in range(depth)],
+                "ev_loaded": [None] * depth,
+                "ev_done": [torch.cuda.Event() for _ in range(depth)],
+                "ev_out": [torch.cuda.Event() for _ in range(depth)],
+            }
+            # order the pipeline after whatever the caller queued on the current stream
+            for st in ("copy", "compute", "out"):
+                self._pipe[st].wait_stream(torch.cuda.current_stream())
+        p = self._pipe
+        ticket = p["next"]
+        slot = ticket % depth
+        p["next"] += 1
+        lib = _native.lib()
+        src = input_signal if isinstance(input_signal, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(input_signal), dtype=np.complex64))
+        with torch.cuda.stream(p["copy"]):
+            if p["ev_loaded"][slot] is not None:          # the slot's previous block has been transformed
+                p["copy"].wait_event(p["ev_loaded"][slot])
+            p["x"][slot].copy_(src, non_blocking=True)
+            p["ev_in"][slot].record(p["copy"])
+        with torch.cuda.stream(p["compute"]):
+            p["compute"].wait_event(p["ev_in"][slot])
+            p["compute"].wait_event(p["ev_out"][slot])    # the slot's previous audio has been read back
+            _native.check(lib.rc_engine_load(self._engine, p["x"][slot].data_ptr(), p["compute"].cuda_stream))
+            ev = torch.cuda.Event()
+            ev.record(p["compute"])
+            p["ev_loaded"][slot] = ev
+            _native.check(lib.rc_engine_run(self._engine, p["audio"][slot].data_ptr(), p["compute"].cuda_stream))
+            p["ev_done"][slot].record(p["compute"])
+        with torch.cuda.stream(p["out"]):
+            p["out"].wait_event(p["ev_done"][slot])
+            p["host"][slot].copy_(p["audio"][slot], non_blocking=True)
+            p["ev_out"][slot].record(p["out"])
+        self._serial += 1
+        self._audio_serial = -1
+        return ticket
+
+    def collect(self, ticket: int):
+        """Packed float32 audio of a submitted block (NumPy view of pinned memory, valid until
+        `depth` more blocks are submitted); ``audio_slices()`` locates each channel."""
+        p = self._pipe
+        if p is None or ticket >= p["next"] or ticket < p["next"] - p["depth"]:
+            raise RuntimeError("unknown or expired ticket")
+        slot = ticket % p["depth"]
+        p["ev_out"][slot].synchronize()
+        return p["host"][slot].numpy()
 
     def audio_slices(self):
         self._ensure_engine()
