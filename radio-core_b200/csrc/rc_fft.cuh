@@ -651,50 +651,69 @@ inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long lon
     return err;
 }
 
-// ---- register-radix schedules (rc_fft3.cuh): X(id, R0, R1, R2, threads, min CTAs/SM) ----
-// (..., column pairs per tile).  R = R0*R1*R2; R1 == 1 marks a two-stage schedule.  A thread owns two columns, so a
-// stage has (R / radix) * 8 butterfly pairs per tile and threads / 8 of them run at once.
-// Kernels are instantiated in rc_fft3_g*.cu, one group per translation unit (id % 4) so
-// they compile in parallel.
-#define RC_V3_GROUP0(X) X(20, 8, 1, 8, 128, 8, 16) X(0, 10, 1, 10, 160, 6, 16) X(4, 10, 1, 16, 256, 3, 16) X(8, 5, 6, 10, 240, 3, 8) X(12, 8, 8, 8, 256, 2, 8) X(16, 8, 10, 10, 320, 2, 8)
-#define RC_V3_GROUP1(X) X(21, 8, 1, 10, 160, 6, 16) X(1, 8, 1, 16, 256, 3, 16) X(5, 4, 5, 10, 400, 2, 16) X(9, 4, 8, 10, 320, 2, 8) X(13, 6, 10, 10, 160, 2, 8) X(17, 10, 10, 10, 400, 1, 8)
-#define RC_V3_GROUP2(X) X(18, 5, 1, 8, 128, 8, 16) X(2, 5, 5, 5, 400, 2, 16) X(6, 5, 5, 10, 400, 2, 16) X(10, 5, 8, 10, 320, 2, 8) X(14, 5, 5, 25, 200, 2, 8)
-#define RC_V3_GROUP3(X) X(19, 5, 1, 10, 160, 6, 16) X(3, 10, 1, 15, 256, 3, 16) X(7, 4, 8, 8, 256, 4, 8) X(11, 5, 10, 10, 200, 3, 8) X(15, 8, 8, 10, 256, 2, 8)
+// ---- register-radix schedules (rc_fft3.cuh):
+//      X(id, R0, R1, R2, threads, min CTAs/SM, column pairs per tile, role) ----
+// R = R0*R1*R2; R1 == 1 marks a two-stage schedule.  A thread owns two columns, so a stage has
+// (R / radix) * CP butterfly pairs per tile and threads / CP of them run at once.
+// role: 0 = any pass, 1 = first pass only, 2 = later passes only.  Short passes exist twice:
+// 16-column tiles for the first pass of a plan (its re-ordered column runs and fused loaders
+// measured faster narrow) and 32-column tiles (256-byte rows) for the later passes.
+// Kernels are instantiated in rc_fft3_g*.cu, one group per translation unit (id % 4) so they
+// compile in parallel.
+#define RC_V3_GROUP0(X) \
+    X(0, 10, 1, 10, 80, 10, 8, 1) X(4, 10, 1, 16, 128, 4, 8, 0) X(8, 5, 6, 10, 240, 3, 8, 0) X(12, 8, 8, 8, 256, 2, 8, 0) \
+    X(16, 8, 10, 10, 320, 2, 8, 0) X(20, 8, 1, 8, 64, 10, 8, 1) X(24, 10, 1, 10, 160, 5, 16, 2) X(32, 8, 1, 8, 128, 8, 16, 2)
+#define RC_V3_GROUP1(X) \
+    X(1, 8, 1, 16, 128, 4, 8, 0) X(5, 4, 5, 10, 200, 4, 8, 0) X(9, 4, 8, 10, 320, 2, 8, 0) X(13, 6, 10, 10, 160, 2, 8, 0) \
+    X(17, 10, 10, 10, 400, 1, 8, 0) X(21, 8, 1, 10, 80, 10, 8, 1) X(33, 8, 1, 10, 160, 5, 16, 2)
+#define RC_V3_GROUP2(X) \
+    X(2, 5, 5, 5, 200, 4, 8, 0) X(6, 5, 5, 10, 200, 4, 8, 0) X(10, 5, 8, 10, 320, 2, 8, 0) X(14, 5, 5, 25, 200, 2, 8, 0) \
+    X(18, 5, 1, 8, 64, 10, 8, 1) X(30, 5, 1, 8, 128, 8, 16, 2)
+#define RC_V3_GROUP3(X) \
+    X(3, 10, 1, 15, 128, 4, 8, 0) X(7, 4, 8, 8, 256, 4, 8, 0) X(11, 5, 10, 10, 200, 3, 8, 0) X(15, 8, 8, 10, 256, 2, 8, 0) \
+    X(19, 5, 1, 10, 80, 10, 8, 1) X(27, 5, 1, 10, 160, 5, 16, 2)
 #define RC_V3_ALL(X) RC_V3_GROUP0(X) RC_V3_GROUP1(X) RC_V3_GROUP2(X) RC_V3_GROUP3(X)
 constexpr int kV3Groups = 4;
 
-struct V3Entry { int id, R0, R1, R2, threads, cp; int R() const { return R0 * R1 * R2; } };
+struct V3Entry { int id, R0, R1, R2, threads, cp, role; int R() const { return R0 * R1 * R2; } };
 inline const std::vector<V3Entry>& v3_table() {
     static const std::vector<V3Entry> t = {
-#define RC_V3_ROW(id, r0, r1, r2, nt, mb, cp) {id, r0, r1, r2, nt, cp},
+#define RC_V3_ROW(id, r0, r1, r2, nt, mb, cp, role) {id, r0, r1, r2, nt, cp, role},
         RC_V3_ALL(RC_V3_ROW)
 #undef RC_V3_ROW
     };
     return t;
 }
-inline const V3Entry* v3_find(int R) {
-    for (const V3Entry& e : v3_table()) if (e.R() == R) return &e;
+// schedule of length R usable as the first (first = true) or as a later pass of a plan
+inline const V3Entry* v3_find(int R, bool first) {
+    for (const V3Entry& e : v3_table())
+        if (e.R() == R && (e.role == 0 || e.role == (first ? 1 : 2))) return &e;
     return nullptr;
 }
+inline bool v3_has(int R) { return v3_find(R, true) && v3_find(R, false); }
 
 // Relative cost of one pass of length R (1.0 = a pass running at the best measured rate;
 // B200, 256 M-point transforms, tools/membench.cu + bench per-kernel timings): small tiles keep
 // many CTAs per SM and overlap their load / compute / store phases, long ones do not.
 inline double fft_pass_cost(int R, bool first) {
     double c;
-    if (R <= 50) c = 1.33;            // tiny tiles: per-CTA fixed costs show
-    else if (R <= 80) c = 1.12;
-    else if (R <= 100) c = 1.0;
-    else if (R <= 125) c = 1.06;
-    else if (R <= 160) c = 0.93;
-    else if (R <= 256) c = 1.0;
-    else if (R <= 400) c = 1.1;
-    else if (R <= 512) c = 1.08;
-    else if (R <= 640) c = 1.05;
-    else if (R <= 800) c = 1.08;
-    else c = 1.65;                    // one CTA per SM
-    if (R == 625) c += 0.15;          // radix-25 stage
-    if (first) c *= R > 640 ? 1.5 : 1.05;   // column runs re-ordered through registers + shared memory
+    if (first) {                      // 16-column tiles; re-ordered column runs
+        if (R <= 50) c = 1.5;
+        else if (R <= 100) c = 1.25;
+        else if (R <= 256) c = 1.05;
+        else if (R <= 400) c = 1.4;
+        else if (R <= 640) c = 1.6;
+        else c = 2.2;
+    } else {
+        if (R <= 50) c = 1.15;        // 32-column tiles for R <= 100
+        else if (R <= 100) c = 1.0;
+        else if (R <= 160) c = 1.15;
+        else if (R <= 256) c = 1.2;
+        else if (R <= 400) c = 1.35;
+        else if (R <= 800) c = 1.3;
+        else c = 2.0;                 // one CTA per SM
+        if (R == 625) c += 0.15;      // radix-25 stage
+    }
     return c;
 }
 
@@ -740,7 +759,7 @@ inline bool fft_choose_fast(long long n, std::vector<int>& Rs) {
                 size_t x = rest.find('x', q);
                 if (x == std::string::npos) x = rest.size();
                 int v = atoi(rest.substr(q, x - q).c_str());
-                if (v <= 0 || !v3_find(v)) { r.clear(); break; }
+                if (v <= 0 || !v3_has(v)) { r.clear(); break; }
                 r.push_back(v);
                 prod *= v;
                 q = x + 1;
@@ -749,7 +768,8 @@ inline bool fft_choose_fast(long long n, std::vector<int>& Rs) {
         }
     }
     if (max_r == (1 << 30) && fft_tuned_split(n, Rs)) return true;
-    for (const V3Entry& e : v3_table()) if (n % e.R() == 0 && e.R() <= max_r) cur.push_back(e.R());
+    for (const V3Entry& e : v3_table())
+        if (n % e.R() == 0 && e.R() <= max_r && e.role != 2 && v3_has(e.R())) cur.push_back(e.R());
     double best = 1e30;
     std::vector<int> pick;
     auto score = [&](const std::vector<int>& r) {
@@ -803,7 +823,8 @@ inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store)
         plan.nfast = (int)Fs.size();
         Ns = 1;
         for (int i = 0; i < plan.nfast; i++) {
-            cudaError_t err = fft_fill_pass(plan.fast[i], n, Fs[i], 2 * v3_find(Fs[i])->cp, Ns, store, v3_find(Fs[i])->id);
+            const V3Entry* ent = v3_find(Fs[i], i == 0);
+            cudaError_t err = fft_fill_pass(plan.fast[i], n, Fs[i], 2 * ent->cp, Ns, store, ent->id);
             if (err != cudaSuccess) return err;
             Ns *= Fs[i];
         }

@@ -206,12 +206,22 @@ cudaError_t v3_run_later(const FftPass& P, const LoadAny& ld, const StoreAny& st
 #endif
 }
 
-#define RC_V3_CASE_FIRST(id, r0, r1, r2, nt, mb, cp)                                                          \
-    case id: return sign < 0 ? v3_run_first<V3Sched<r0, r1, r2, nt, mb, cp>, -1>(P, ld, st, batch, stream)    \
-                             : v3_run_first<V3Sched<r0, r1, r2, nt, mb, cp>, +1>(P, ld, st, batch, stream);
-#define RC_V3_CASE_LATER(id, r0, r1, r2, nt, mb, cp)                                                          \
-    case id: return sign < 0 ? v3_run_later<V3Sched<r0, r1, r2, nt, mb, cp>, -1>(P, ld, st, batch, stream)    \
-                             : v3_run_later<V3Sched<r0, r1, r2, nt, mb, cp>, +1>(P, ld, st, batch, stream);
+// role (rc_fft.cuh): schedules restricted to one kind of pass instantiate only that kernel
+template <class S, int ROLE>
+cudaError_t v3_role_first(int sign, const FftPass& P, const LoadAny& ld, const StoreC64& st, int batch, cudaStream_t stream) {
+    if constexpr (ROLE == 2) return cudaErrorInvalidValue;
+    else return sign < 0 ? v3_run_first<S, -1>(P, ld, st, batch, stream) : v3_run_first<S, +1>(P, ld, st, batch, stream);
+}
+template <class S, int ROLE>
+cudaError_t v3_role_later(int sign, const FftPass& P, const LoadAny& ld, const StoreAny& st, int batch, cudaStream_t stream) {
+    if constexpr (ROLE == 1) return cudaErrorInvalidValue;
+    else return sign < 0 ? v3_run_later<S, -1>(P, ld, st, batch, stream) : v3_run_later<S, +1>(P, ld, st, batch, stream);
+}
+
+#define RC_V3_CASE_FIRST(id, r0, r1, r2, nt, mb, cp, role) \
+    case id: return v3_role_first<V3Sched<r0, r1, r2, nt, mb, cp>, role>(sign, P, ld, st, batch, stream);
+#define RC_V3_CASE_LATER(id, r0, r1, r2, nt, mb, cp, role) \
+    case id: return v3_role_later<V3Sched<r0, r1, r2, nt, mb, cp>, role>(sign, P, ld, st, batch, stream);
 
 #define RC_V3_DEFINE_GROUP(k, LIST)                                                                           \
     cudaError_t v3_first_g##k(int id, int sign, const FftPass& P, const LoadAny& ld, const StoreC64& st,      \
