@@ -460,13 +460,25 @@ __global__ void __launch_bounds__(512) fft_pass_kernel(const FftPass P, const Lo
 #endif
 
 // ------------------------------------------------------------------- planning
+struct TableStore;
 struct FftPlan {
     long long n = 0;
     int npass = 0;                 // generic shared-memory passes (any 2^a 3^b 5^c size)
     FftPass pass[kMaxPasses];
-    int nfast = 0;                 // register-radix passes (rc_fft2.cuh) when n splits into curated lengths
+    int nfast = 0;                 // register-radix passes (rc_fft3.cuh) when n splits into curated lengths
     FftPass fast[kMaxPasses];
     int max_passes() const { return npass > nfast ? npass : nfast; }
+    // fused last two passes (rc_fused.cuh): L2-resident ring + per-chunk counters
+    struct Fuse {
+        bool ok = false;
+        int W = 32, lag = 6, nslot = 12;
+        float2* ring = nullptr;
+        long long slot_elems = 0;
+        int* counters = nullptr;       // [err | doneA[cap] | doneB[cap]]
+        long long cap = 0;
+    };
+    mutable Fuse fuse;
+    struct TableStore* store = nullptr;
 };
 
 // Memory source for the plan tables: device (product) or host (CPU emulation).
@@ -500,6 +512,19 @@ struct TableStore {
         return p;
     }
     bool has(const std::string& key) const { return cache.count(key) != 0; }
+    // uninitialised scratch owned by the store (zero-filled)
+    void* alloc(size_t bytes, cudaError_t* err) {
+        void* p = nullptr;
+        if (on_device) {
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+            if (e != cudaSuccess) { if (err) *err = e; return nullptr; }
+        } else {
+            p = calloc(1, bytes);
+        }
+        owned.push_back(p);
+        return p;
+    }
 };
 
 inline bool fft_size_supported(long long n) {
@@ -675,6 +700,15 @@ inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long lon
 #define RC_V3_ALL(X) RC_V3_GROUP0(X) RC_V3_GROUP1(X) RC_V3_GROUP2(X) RC_V3_GROUP3(X)
 constexpr int kV3Groups = 4;
 
+// (pass A id, pass B id) pairs the fused last-two-passes kernel (rc_fused.cuh) is compiled for
+#define RC_FUSED_LIST(X) X(24, 24) X(27, 24) X(27, 27)
+inline bool v3_fused_supported(int id_a, int id_b) {
+#define RC_FUSED_Q(a, b) if (id_a == a && id_b == b) return true;
+    RC_FUSED_LIST(RC_FUSED_Q)
+#undef RC_FUSED_Q
+    return false;
+}
+
 struct V3Entry { int id, R0, R1, R2, threads, cp, role; int R() const { return R0 * R1 * R2; } };
 inline const std::vector<V3Entry>& v3_table() {
     static const std::vector<V3Entry> t = {
@@ -827,6 +861,21 @@ inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store)
             cudaError_t err = fft_fill_pass(plan.fast[i], n, Fs[i], 2 * ent->cp, Ns, store, ent->id);
             if (err != cudaSuccess) return err;
             Ns *= Fs[i];
+        }
+        plan.store = &store;
+        const int na = plan.nfast - 2, nb = plan.nfast - 1;
+        if (plan.nfast >= 3 && !getenv("RC_NO_FUSE") && n < (1LL << 31) &&
+            v3_fused_supported(plan.fast[na].fast_id, plan.fast[nb].fast_id)) {
+            FftPlan::Fuse& fz = plan.fuse;
+            if (const char* env = getenv("RC_FUSE_LAG")) fz.lag = atoi(env);
+            if (const char* env = getenv("RC_FUSE_NSLOT")) fz.nslot = atoi(env);
+            if (fz.lag < 1) fz.lag = 1;
+            if (fz.nslot <= fz.lag) fz.nslot = fz.lag + 2;
+            fz.slot_elems = (long long)plan.fast[na].R * plan.fast[nb].R * fz.W;
+            cudaError_t err = cudaSuccess;
+            fz.ring = (float2*)store.alloc((size_t)fz.nslot * fz.slot_elems * sizeof(float2), &err);
+            if (err != cudaSuccess) return err;
+            fz.ok = fz.ring != nullptr;
         }
     }
     return cudaSuccess;

@@ -203,18 +203,36 @@ RC_HD void v3_stage1(float4* tile, const float2* tw, int tid) {
     }
 }
 
+// Where the outputs of one column pair of a later pass go: element K of column A at
+// oa + K*ns, of column B at ob + K*ns (default: the Stockham position in the batch entry;
+// the fused pass pairs of rc_fused.cuh point it into their L2-resident ring instead).
+struct V3Out {
+    long long oa, ob, ns;
+    bool act_a, act_b, pair;
+};
+
+template <class S>
+RC_HD V3Out v3_out_default(const FftPass& P, long long j0, int tid) {
+    const int cp = tid & (S::CP - 1);
+    const long long j = j0 + 2 * cp;
+    V3Out o;
+    o.act_a = j < P.stride;
+    o.act_b = j + 1 < P.stride;
+    o.ns = P.Ns;
+    const long long qn = j / o.ns, rem = j - qn * o.ns;
+    o.oa = qn * o.ns * S::R + rem;
+    o.ob = (rem + 1 < o.ns) ? o.oa + 1 : (qn + 1) * o.ns * S::R;
+    o.pair = P.pair_ok && o.act_b;
+    return o;
+}
+
 // last stage, passes after the first: radix R2 over digit d2, results straight to global
 template <class S, int SIGN, class StoreOp>
-RC_HD void v3_last_direct(const float4* tile, const FftPass& P, const StoreOp& st, int batch, long long j0, int tid) {
+RC_HD void v3_last_direct(const float4* tile, const StoreOp& st, int batch, const V3Out& o, int tid) {
     const int cp = tid & (S::CP - 1), g = tid >> S::LOGCP;
-    const long long j = j0 + 2 * cp;
-    if (j >= P.stride) return;
-    const bool act_b = j + 1 < P.stride;
-    const long long ns = P.Ns;
-    const long long qn = j / ns, rem = j - qn * ns;
-    const long long oa = qn * ns * S::R + rem;
-    const long long ob = (rem + 1 < ns) ? oa + 1 : (qn + 1) * ns * S::R;
-    const bool pair = P.pair_ok && act_b;
+    if (!o.act_a) return;
+    const long long ns = o.ns, oa = o.oa, ob = o.ob;
+    const bool act_b = o.act_b, pair = o.pair;
 #pragma unroll
     for (int it = 0; it < S::IT2; it++) {
         const int q = g + it * S::NG;
@@ -243,6 +261,10 @@ RC_HD void v3_last_direct(const float4* tile, const FftPass& P, const StoreOp& s
             }
         }
     }
+}
+template <class S, int SIGN, class StoreOp>
+RC_HD void v3_last_direct(const float4* tile, const FftPass& P, const StoreOp& st, int batch, long long j0, int tid) {
+    v3_last_direct<S, SIGN>(tile, st, batch, v3_out_default<S>(P, j0, tid), tid);
 }
 
 // last stage of the first pass, part A: read + radix into held registers
