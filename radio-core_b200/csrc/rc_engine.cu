@@ -834,6 +834,17 @@ int rc_pll_eval(rc_pll* p, double mult, int imag, float* outp, void* stream) {
     return RC_OK;
 }
 
+// Non-zero when a fused-pass kernel gave up waiting for a dependency (results of that call are
+// invalid); cleared by the call.  Never expected: the tile queue is ordered so that every
+// dependency is issued first.
+int rc_fused_errors(void) {
+    int* w = fused_error_word(false);
+    if (!w) return 0;
+    const int v = *w;
+    *w = 0;
+    return v;
+}
+
 // ------------------------------------------------------------------ profiling
 int rc_profile_enable(int on) {
     Profiler& p = profiler();

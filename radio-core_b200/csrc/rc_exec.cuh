@@ -114,6 +114,26 @@ struct FusedPair {
 cudaError_t v3_fused_dispatch(int id_a, int id_b, int sign, const FusedPair& f, const LoadAny& ld_a, const StoreAny& st_b,
                               cudaStream_t stream);
 
+// Error word of the fused kernels (a dependency wait that ran out of budget): host-mapped, so the
+// host can poll it without synchronising (rc_fused_errors()).
+inline int* fused_error_word(bool device_view) {
+    static int* host = nullptr;
+    static int* dev = nullptr;
+    if (!host) {
+#ifdef RC_EMULATE
+        host = dev = (int*)calloc(1, sizeof(int));
+#else
+        if (cudaHostAlloc((void**)&host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+            *host = 0;
+            if (cudaHostGetDevicePointer((void**)&dev, host, 0) != cudaSuccess) dev = nullptr;
+        } else {
+            host = nullptr;
+        }
+#endif
+    }
+    return device_view ? dev : host;
+}
+
 // Fill the pair for `batch` transforms; (re)allocates the chunk counters when the batch grows.
 inline cudaError_t fused_prepare(const FftPlan& plan, int batch, FusedPair& f) {
     const FftPass& PA = plan.fast[plan.nfast - 2];
@@ -135,7 +155,8 @@ inline cudaError_t fused_prepare(const FftPlan& plan, int batch, FusedPair& f) {
         if (err != cudaSuccess || !fz.counters) return err != cudaSuccess ? err : cudaErrorMemoryAllocation;
         fz.cap = f.nchunks;
     }
-    f.err = fz.counters;
+    f.err = fused_error_word(true);
+    if (!f.err) f.err = fz.counters;             // no mapped memory: keep the flag on the device
     f.doneA = fz.counters + 4;
     f.doneB = f.doneA + f.nchunks;
     return cudaSuccess;

@@ -106,8 +106,7 @@ __device__ __forceinline__ void fused_wait(const int* cnt, int target, int* err)
 
 template <class SA, class SB> struct FusedCfg {
     static constexpr int NT = SA::NT > SB::NT ? SA::NT : SB::NT;
-    static constexpr int MINB_ = SA::MINB < SB::MINB ? SA::MINB : SB::MINB;
-    static constexpr int MINB = MINB_ > 4 ? 4 : MINB_;      // both roles + the queue bookkeeping in one kernel: leave registers
+    static constexpr int MINB = SA::MINB < SB::MINB ? SA::MINB : SB::MINB;
     static constexpr int SMEM = SA::SMEM_BYTES > SB::SMEM_BYTES ? SA::SMEM_BYTES : SB::SMEM_BYTES;
 };
 
@@ -122,6 +121,10 @@ v3_fused_ll_kernel(const FusedPair f, const LoadAny ldA, const StoreAny stB, con
     const FusedTile t = fused_tile(f, it);
     const int tid = threadIdx.x;
     float4* tile = (float4*)rc_v3_smem;
+    if (t.valid == 0) {                              // tile past the last column of a partial chunk: bookkeeping only
+        if (tid == 0) atomicAdd((it.role == 0 ? f.doneA : f.doneB) + it.chunk, 1);
+        return;
+    }
     if (it.role == 0) {
         float2* tw = (float2*)(rc_v3_smem + (size_t)SA::TILE_F4 * 16);
         uint64_t* bar = (uint64_t*)(tw + SA::R);
@@ -144,17 +147,14 @@ v3_fused_ll_kernel(const FusedPair f, const LoadAny ldA, const StoreAny stB, con
             const StoreC64 ring{f.ring + (long long)t.slot * f.slot_elems, 0, 1.0f};
             v3_last_direct<SA, SIGN>(tile, ring, 0, fused_out_ring<SA>(f, t, tid), tid);
         }
-        __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(f.doneA + it.chunk, 1);
+        if (tid == 0) {                               // cumulative fence: covers the CTA's stores ordered by the barrier
+            __threadfence();
+            atomicAdd(f.doneA + it.chunk, 1);
+        }
     } else {
         float2* tw = (float2*)(rc_v3_smem + (size_t)SB::TILE_F4 * 16);
         uint64_t* bar = (uint64_t*)(tw + SB::R);
-        V3Tw tws;
-        if (tid < SB::NT) {
-            v3_load_table<SB, SIGN>(tw, f.PB, tid);
-            tws = v3_twiddle_setup<SB, true>(f.PB, t.j0, tid);
-        }
         if (tid == 0) {
             fused_wait(f.doneA + it.chunk, f.nA, f.err);                 // chunk complete?
             asm volatile("fence.proxy.async;" ::: "memory");             // generic-proxy stores -> TMA reads
@@ -163,6 +163,11 @@ v3_fused_ll_kernel(const FusedPair f, const LoadAny ldA, const StoreAny stB, con
             const int x = 2 * (t.row * f.W + t.w * SB::T);
             for (int r = 0; r < SB::R; r += f.box_rows)
                 tma_load_3d(tile + (size_t)r * SB::CP, &tmapR, bar, x, r, t.slot);
+        }
+        V3Tw tws;
+        if (tid < SB::NT) {
+            v3_load_table<SB, SIGN>(tw, f.PB, tid);
+            tws = v3_twiddle_setup<SB, true>(f.PB, t.j0, tid);
         }
         __syncthreads();
         mbar_wait(bar, 0);
@@ -195,6 +200,7 @@ cudaError_t v3_run_fused_ll(const FusedPair& f, const LoadAny& ldA, const StoreA
     for (long long ticket = 0; ticket < f.total(); ticket++) {
         const FusedItem it = fused_decode(f, ticket);
         const FusedTile t = fused_tile(f, it);
+        if (t.valid == 0) continue;
         if (it.role == 0) {
             float2* tw = (float2*)(tile + SA::TILE_F4);
             for (int tid = 0; tid < SA::NT; tid++) v3_load_table<SA, SIGN>(tw, f.PA, tid);

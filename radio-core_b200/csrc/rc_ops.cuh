@@ -130,6 +130,8 @@ struct LoadTunerGather {
         if (s >= c.nx) s -= c.nx;
         unsigned s1 = s + 1u + (i == c.half ? c.gap : 0u);
         if (s1 >= c.nx) s1 -= c.nx;
+        // (a 16-byte fast path for the aligned common case measured no faster at config 3 and
+        // slower, through divergence, for rolls of mixed parity: configs 2 and 4)
         float2 a = cscale(ldg(X + s), ldg(wtab + i));
         float2 d = make_float2(0.f, 0.f);
         if (has_b) d = cscale(ldg(X + s1), ldg(wtab + i + 1));

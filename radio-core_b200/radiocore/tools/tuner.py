@@ -259,7 +259,13 @@ class Tuner:
             raise RuntimeError("unknown or expired ticket")
         slot = ticket % p["depth"]
         p["ev_out"][slot].synchronize()
+        self._check_health()
         return p["host"][slot].numpy()
+
+    @staticmethod
+    def _check_health():
+        if _native.lib().rc_fused_errors():
+            raise RuntimeError("radiocore (B200): a fused FFT pass abandoned a dependency wait; block invalid")
 
     def audio_slices(self):
         self._ensure_engine()
@@ -279,6 +285,7 @@ class Tuner:
             return
         self._audio_host.copy_(self._audio_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        self._check_health()
         self._host_serial = self._serial
 
     def _channel_iq(self, index, serial):

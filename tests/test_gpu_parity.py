@@ -195,3 +195,25 @@ def test_block_pipeline_matches_synchronous_path(rc):
         assert np.array_equal(a, b)
     with pytest.raises(RuntimeError):
         pipe_t.collect(0)                       # expired ticket
+
+
+@pytest.mark.parametrize("n,batch", [(500_000, 3), (1_000_000, 2)])
+def test_fused_last_two_passes_gpu(rc, n, batch, monkeypatch):
+    """Opt-in fused last-two-passes kernel (RC_FUSE=1): same numbers as the separate passes, no
+    abandoned dependency waits."""
+    import torch
+    from radiocore import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    outs = []
+    for fuse in (False, True):
+        if fuse:
+            monkeypatch.setenv("RC_FUSE", "1")
+        out = torch.empty_like(xd)
+        _native.check(lib.rc_fft_c2c(0, n, batch, -1, xd.data_ptr(), out.data_ptr(), None))
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    assert lib.rc_fused_errors() == 0
+    assert np.array_equal(outs[0], outs[1])

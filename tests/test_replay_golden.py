@@ -102,3 +102,20 @@ def test_error_codes(emu):
         emu.WBFM(30000, 6000)                        # 19 kHz pilot above Nyquist
     with pytest.raises(ValueError):
         emu.Bandpass(100, 10, 20, num_taps=61).run(np.zeros(100))   # shorter than padlen
+
+
+@pytest.mark.parametrize("n,batch", [(500_000, 2), (1_000_000, 1), (2_560_000, 1)])
+def test_fused_last_two_passes_replay(emu, n, batch, monkeypatch):
+    """rc_fused.cuh (opt-in, RC_FUSE=1): the tile queue, ring layout and partial chunks of the fused
+    last-two-passes kernel, replayed on the CPU in queue order, give the same transform (bit for
+    bit: the arithmetic is that of the two separate passes)."""
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    plain = emu.fft(x, -1)
+    monkeypatch.setenv("RC_FUSE", "1")
+    monkeypatch.setenv("RC_FUSE_LAG", "2")
+    monkeypatch.setenv("RC_FUSE_NSLOT", "3")          # ring re-use after 3 chunks
+    fused = emu.fft(x, -1)
+    assert np.array_equal(plain, fused)
+    ref = np.fft.fft(x.astype(np.complex128), axis=1)
+    assert np.max(np.abs(fused - ref)) / np.sqrt(np.mean(np.abs(ref) ** 2)) < 3e-6
