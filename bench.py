@@ -421,7 +421,7 @@ def run_b200(args, rank, world, local_rank):
             "kernels": table, "clocks": clocks}
     if e2e:
         line["e2e"] = {"value": samples_per_step * args.steps / t_e2e / 1e6, "unit": UNIT,
-                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                       "h2d_bytes_per_step": e2e["h2d"] * streams, "d2h_bytes_per_step": e2e["d2h"] * streams,
                        "ms_per_step": t_e2e / args.steps * 1e3, "timing": "wall clock between device synchronisations, max over ranks",
                        "api": "Tuner.submit()/collect(): pinned host IQ -> H2D -> kernels -> D2H of all channels' audio, 2 blocks in flight"}
     if world == 1 and not args.no_cpu_baseline:
@@ -450,6 +450,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: one JSON line only
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:

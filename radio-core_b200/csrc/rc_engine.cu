@@ -283,7 +283,7 @@ struct DemodBank {
             if (mode == RC_MODE_FM) return RC_OK;
         } else {
             // mpx = FM(B, B): same-size resample = folded Hamming taper (wbfm.py:42-43,77)
-            RC_API_CUDA(launch_ew(h, batch, SpecResampleEw{specBB, Z1, ZpB}, st, "wbfm.spec_taper", 16.0 * h * batch),
+            RC_API_CUDA(launch_ew(h / 2 + 1, batch, SpecTaperPairEw{specBB, Z1, ZpB}, st, "wbfm.spec_taper", 16.0 * h * batch),
                         "spec B->B");
             RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreC64{(float2*)mpx, h, 1.0f}, w0, w1, st,
                                   "wbfm.irfft_mpx")), "ifft mpx");
@@ -292,7 +292,7 @@ struct DemodBank {
             // PLL.step (hilbert) + image(2) * mpx * 1.0175      (wbfm.py:80-83)
             RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadC64{(const float2*)pilot, h}, StoreC64{Z2, h, 1.0f}, w0, w1, st,
                                   "wbfm.rfft_pilot")), "fft pilot");
-            RC_API_CUDA(launch_ew(h, batch, SpecHilbertEw{specH, Z2, ZpB}, st, "wbfm.spec_hilbert", 16.0 * h * batch),
+            RC_API_CUDA(launch_ew(h / 2 + 1, batch, SpecHilbertPairEw{specH, Z2, ZpB}, st, "wbfm.spec_hilbert", 16.0 * h * batch),
                         "spec hilbert");
             RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreLmrPacked{pilot, mpx, lmr, B}, w0, w1, st,
                                   "wbfm.irfft_hilbert_lmr", 0.0, 12.0 * B * batch)), "ifft hilbert");
@@ -821,7 +821,7 @@ int rc_pll_step(rc_pll* p, const float* in, void* stream) {
     DeviceGuard g(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     RC_API_CUDA((fft_exec<-1>(p->plan, 1, LoadC64{(const float2*)in, p->h}, StoreC64{p->Z, p->h, 1.0f}, p->w0, p->w1, st)), "fft");
-    RC_API_CUDA(launch_ew(p->h, 1, SpecHilbertEw{p->spec, p->Z, p->Zp}, st), "hilbert");
+    RC_API_CUDA(launch_ew(p->h / 2 + 1, 1, SpecHilbertPairEw{p->spec, p->Z, p->Zp}, st), "hilbert");
     RC_API_CUDA((fft_exec<+1>(p->plan, 1, LoadC64{p->Zp, p->h}, StoreAnalyticPacked{in, p->z, p->n}, p->w0, p->w1, st)), "ifft");
     p->stepped = true;
     return RC_OK;

@@ -94,23 +94,31 @@ template <int SIGN> RC_HD float2 v3_tw32(double2 w) {
 // behind the TMA load.
 struct V3Tw { double2 wa, wb, sta, stb, wsa, wsb; };
 
+// W_M^q for q < M < 2^32 (always the case here: q <= U*(Ns-1) < M/R0): 32-bit index arithmetic
+RC_HD double2 v3_tw64(const FftPass& P, unsigned q) {
+    const double2 a = ldg(P.tw_lo + (q & P.tw_mask));
+    const double2 b = ldg(P.tw_hi + (q >> P.tw_shift));
+    return cmul64(a, b);
+}
+
 template <class S, bool LATER>
 RC_HD V3Tw v3_twiddle_setup(const FftPass& P, long long j0, int tid) {
     V3Tw t;
     t.wa = t.wb = t.sta = t.stb = t.wsa = t.wsb = make_double2(1.0, 0.0);
     if (LATER) {
         const int cp = tid & (S::CP - 1), g = tid >> S::LOGCP;
-        const unsigned long long ns = (unsigned long long)P.Ns;
-        const unsigned long long ka = (unsigned long long)(j0 + 2 * cp) % ns;
-        const unsigned long long kb = (ka + 1 == ns) ? 0 : ka + 1;
-        t.wa = fft_tw64(P, (unsigned long long)g * ka);
-        t.wb = fft_tw64(P, (unsigned long long)g * kb);
-        if (S::IT0 > 1) {
-            t.sta = fft_tw64(P, (unsigned long long)S::NG * ka);
-            t.stb = fft_tw64(P, (unsigned long long)S::NG * kb);
-        }
-        t.wsa = fft_tw64(P, (unsigned long long)S::U * ka);
-        t.wsb = fft_tw64(P, (unsigned long long)S::U * kb);
+        const unsigned ns = (unsigned)P.Ns;
+        const unsigned ka = (unsigned)(j0 + 2 * cp) % ns;
+        // column A from the two-level table; column B = A's twiddle times W^{g}, W^{NG}, W^{U}
+        // (kb = ka + 1), which are the same for every column: three short look-ups
+        t.wa = v3_tw64(P, (unsigned)g * ka);
+        t.wsa = v3_tw64(P, (unsigned)S::U * ka);
+        if (S::IT0 > 1) t.sta = v3_tw64(P, (unsigned)S::NG * ka);
+        if (ka + 1u != ns) {
+            t.wb = cmul64(t.wa, v3_tw64(P, (unsigned)g));
+            t.wsb = cmul64(t.wsa, v3_tw64(P, (unsigned)S::U));
+            if (S::IT0 > 1) t.stb = cmul64(t.sta, v3_tw64(P, (unsigned)S::NG));
+        }                                   // else kb = 0: all ones
     }
     return t;
 }

@@ -351,6 +351,38 @@ struct SpecResampleEw {
     }
 };
 
+// Same-size variants (num == n_x, so hp == h) that produce bins k and h-k together: both need
+// exactly Z[k] and Z[h-k], and the twiddles of h-k are -conj of those of k, so one thread loads
+// four values for two outputs instead of ten.  Launch over k in [0, h/2].
+RC_HD float2 rfft_from(float2 zk, float2 zm_conj, float2 tw) {
+    const float2 e = make_float2(0.5f * (zk.x + zm_conj.x), 0.5f * (zk.y + zm_conj.y));
+    const float2 dlt = make_float2(0.5f * (zk.x - zm_conj.x), 0.5f * (zk.y - zm_conj.y));
+    return cadd(e, cmul(tw, make_float2(dlt.y, -dlt.x)));
+}
+
+struct SpecTaperPairEw {          // SpecResampleEw with s.num == s.n_x  (FM(B, B) taper, wbfm.py:42-43)
+    RealResampleSpec s;
+    const float2* Z;
+    float2* Zp;
+    RC_HD void operator()(int b, long long k) const {
+        const float2* z = Z + b * s.h;
+        float2* o = Zp + b * s.h;
+        const long long km = s.h - k;
+        if (k == 0 || k == km) {                       // DC (pairs with Nyquist) and the self-paired middle bin
+            o[k] = irfft_pack(s.bin(z, k, 1), cconj(s.bin(z, s.hp - k, 1)), ldg(s.itw + k));
+            return;
+        }
+        const float2 zk = ldg(z + k), zm = ldg(z + km);
+        const float2 rt = ldg(s.rtw + k), it = ldg(s.itw + k);
+        const float2 rtm = make_float2(-rt.x, rt.y), itm = make_float2(-it.x, it.y);      // -conj
+        const float wk = (s.a0 + s.a1c * rt.x) * s.scale, wm = (s.a0 - s.a1c * rt.x) * s.scale;
+        const float2 bk = cscale(rfft_from(zk, cconj(zm), rt), wk);
+        const float2 bm = cscale(rfft_from(zm, cconj(zk), rtm), wm);
+        o[k] = irfft_pack(bk, cconj(bm), it);
+        o[km] = irfft_pack(bm, cconj(bk), itm);
+    }
+};
+
 // WBFM audio spectra (wbfm.py:86-87 with linearity of Decimate):
 // L = D(mpx)+D(lmr), R = D(mpx)-D(lmr);  rfft(mpx)[k] = X_d[k]*Wf[k]  (the
 // same-size FM(B,B) resample, wbfm.py:42-43), so D(mpx) carries Wf twice.
@@ -389,6 +421,27 @@ struct SpecHilbertEw {
     }
 };
 
+struct SpecHilbertPairEw {        // SpecHilbertEw, bins k and h-k together; launch over k in [0, h/2]
+    RealResampleSpec s;
+    const float2* Z;
+    float2* Zp;
+    RC_HD void operator()(int b, long long k) const {
+        const float2* z = Z + b * s.h;
+        float2* o = Zp + b * s.h;
+        const long long km = s.h - k;
+        SpecHilbertEw one{s, Z, Zp};
+        if (k == 0 || k == km) { one(b, k); return; }
+        const float2 zk = ldg(z + k), zm = ldg(z + km);
+        const float2 rt = ldg(s.rtw + k), it = ldg(s.itw + k);
+        const float2 rtm = make_float2(-rt.x, rt.y), itm = make_float2(-it.x, it.y);
+        const float2 pk = rfft_from(zk, cconj(zm), rt), pm = rfft_from(zm, cconj(zk), rtm);
+        const float2 hk = make_float2(pk.y * s.scale, -pk.x * s.scale);        // -i * P
+        const float2 hm = make_float2(pm.y * s.scale, -pm.x * s.scale);
+        o[k] = irfft_pack(hk, cconj(hm), it);
+        o[km] = irfft_pack(hm, cconj(hk), itm);
+    }
+};
+
 // StoreOp of the Hilbert inverse FFT: element i carries (hhat[2i], hhat[2i+1]).
 // pll.py:57-58 image(2) = Im(z^2)/|z^2| = 2 p hhat / (p^2 + hhat^2);
 // wbfm.py:83 lmr = image(2) * mpx * 1.0175.
@@ -398,7 +451,11 @@ struct StoreLmrPacked {
     float* lmr;           // [batch][n]
     long long n;
     RC_HD static float one(float p, float hh, float m) {
+#ifdef __CUDA_ARCH__
+        const float s2 = __fdividef(2.0f * p * hh, p * p + hh * hh);     // 0/0 -> NaN like the reference
+#else
         const float s2 = (2.0f * p * hh) / (p * p + hh * hh);
+#endif
         return s2 * m * 1.0175f;
     }
     RC_HD void operator()(int b, long long i, float2 v) const {
