@@ -137,16 +137,23 @@ class ClockSampler(threading.Thread):
     def run(self):
         if self.nv is None:
             return
+        n = 0
         while not self.stop_flag:
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-            except Exception:
-                pass
-            time.sleep(0.05)
+            self._sample()
+            n += 1
+            time.sleep(0.002 if n < 50 else 0.05)      # short timed regions (config 2: a few ms) still get samples
+
+    def _sample(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        except Exception:
+            pass
 
     def summary(self):
         self.stop_flag = True
+        if self.nv is not None and not self.samples:
+            self._sample()                              # region shorter than the thread's start-up
         if self.nv is None or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,

@@ -227,7 +227,8 @@ RC_HD V3Out v3_out_default(const FftPass& P, long long j0, int tid) {
     o.act_a = j < P.stride;
     o.act_b = j + 1 < P.stride;
     o.ns = P.Ns;
-    const long long qn = j / o.ns, rem = j - qn * o.ns;
+    const unsigned qn32 = (unsigned)j / (unsigned)P.Ns;          // n < 2^31 on this path: 32-bit division
+    const long long qn = qn32, rem = j - qn * o.ns;
     o.oa = qn * o.ns * S::R + rem;
     o.ob = (rem + 1 < o.ns) ? o.oa + 1 : (qn + 1) * o.ns * S::R;
     o.pair = P.pair_ok && o.act_b;

@@ -646,12 +646,17 @@ RC_HD int fir_slot(int i) { return i + (i >> 3); }
 constexpr int kFirSlots = kFirChunk + kFirMaxTaps + 8 + (kFirChunk + kFirMaxTaps + 8) / 8 + 1;
 
 #if defined(__CUDACC__) && !defined(RC_EMULATE)
-__device__ __forceinline__ void fir_window8(const double* xs, const double* taps, int ntaps8, int o, double acc[kFirPer]) {
+// NT8 > 0: tap count known at compile time (fully unrolled: the sliding window lives in renamed
+// registers, no moves); NT8 == 0: runtime count.
+template <int NT8>
+__device__ __forceinline__ void fir_window8_t(const double* xs, const double* taps, int ntaps8, int o, double acc[kFirPer]) {
     double w[16];
     const double* x0 = xs + fir_slot(o);           // o is a multiple of 8: groups are contiguous
 #pragma unroll
     for (int i = 0; i < 8; i++) w[i] = x0[i];
-    for (int j0 = 0; j0 < ntaps8; j0 += 8) {
+    const int n8 = NT8 > 0 ? NT8 : ntaps8;
+#pragma unroll
+    for (int j0 = 0; j0 < n8; j0 += 8) {
         const double* x1 = xs + fir_slot(o + j0 + 8);
 #pragma unroll
         for (int i = 0; i < 8; i++) w[8 + i] = x1[i];
@@ -664,6 +669,11 @@ __device__ __forceinline__ void fir_window8(const double* xs, const double* taps
 #pragma unroll
         for (int i = 0; i < 8; i++) w[i] = w[8 + i];
     }
+}
+__device__ __forceinline__ void fir_window8(const double* xs, const double* taps, int ntaps8, int o, double acc[kFirPer]) {
+    if (ntaps8 == 88) fir_window8_t<88>(xs, taps, ntaps8, o, acc);          // 81-tap pilot filter (41 (*) 41)
+    else if (ntaps8 == 56) fir_window8_t<56>(xs, taps, ntaps8, o, acc);     // 51-tap de-emphasis
+    else fir_window8_t<0>(xs, taps, ntaps8, o, acc);
 }
 
 // Phase 1 of the audio epilogue: de-emphasis FIR of one chunk, fp64 staging, per-chunk sum.
