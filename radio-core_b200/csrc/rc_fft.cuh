@@ -685,31 +685,18 @@ inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long lon
 // measured faster narrow) and 32-column tiles (256-byte rows) for the later passes.
 // Kernels are instantiated in rc_fft3_g*.cu, one group per translation unit (id % 4) so they
 // compile in parallel.
-// experiment: first passes of length 200 as 8*5*5 (eight rows of loads in flight per butterfly)
-#ifdef RC_R200_855
-#define RC_R200_ROLE 2
-#define RC_R200_FIRST(X) X(34, 8, 5, 5, 200, 4, 8, 1)
-#else
-#define RC_R200_ROLE 0
-#define RC_R200_FIRST(X)
-#endif
-#ifdef RC_SMALL_NT
-#define RC_WNT(a, b) b
-#else
-#define RC_WNT(a, b) a
-#endif
 #define RC_V3_GROUP0(X) \
     X(0, 10, 1, 10, 80, 10, 8, 1) X(4, 10, 1, 16, 128, 4, 8, 0) X(8, 5, 6, 10, 240, 3, 8, 0) X(12, 8, 8, 8, 256, 2, 8, 0) \
-    X(16, 8, 10, 10, 320, 2, 8, 0) X(20, 8, 1, 8, 64, 10, 8, 1) X(24, 10, 1, 10, RC_WNT(160, 80), RC_WNT(5, 8), 16, 2) X(32, 8, 1, 8, RC_WNT(128, 64), RC_WNT(8, 10), 16, 2)
+    X(16, 8, 10, 10, 320, 2, 8, 0) X(20, 8, 1, 8, 64, 10, 8, 1) X(24, 10, 1, 10, 160, 5, 16, 2) X(32, 8, 1, 8, 128, 8, 16, 2)
 #define RC_V3_GROUP1(X) \
-    X(1, 8, 1, 16, 128, 4, 8, 0) X(5, 4, 5, 10, 200, 4, 8, RC_R200_ROLE) X(9, 4, 8, 10, 320, 2, 8, 0) X(13, 6, 10, 10, 160, 2, 8, 0) \
-    X(17, 10, 10, 10, 400, 1, 8, 0) X(21, 8, 1, 10, 80, 10, 8, 1) X(33, 8, 1, 10, RC_WNT(160, 80), RC_WNT(5, 8), 16, 2)
+    X(1, 8, 1, 16, 128, 4, 8, 0) X(5, 4, 5, 10, 200, 4, 8, 0) X(9, 4, 8, 10, 320, 2, 8, 0) X(13, 6, 10, 10, 160, 2, 8, 0) \
+    X(17, 10, 10, 10, 400, 1, 8, 0) X(21, 8, 1, 10, 80, 10, 8, 1) X(33, 8, 1, 10, 160, 5, 16, 2)
 #define RC_V3_GROUP2(X) \
     X(2, 5, 5, 5, 200, 4, 8, 0) X(6, 5, 5, 10, 200, 4, 8, 0) X(10, 5, 8, 10, 320, 2, 8, 0) X(14, 5, 5, 25, 200, 2, 8, 0) \
-    X(18, 5, 1, 8, 64, 10, 8, 1) RC_R200_FIRST(X) X(30, 5, 1, 8, RC_WNT(128, 64), RC_WNT(8, 10), 16, 2)
+    X(18, 5, 1, 8, 64, 10, 8, 1) X(30, 5, 1, 8, 128, 8, 16, 2)
 #define RC_V3_GROUP3(X) \
     X(3, 10, 1, 15, 128, 4, 8, 0) X(7, 4, 8, 8, 256, 4, 8, 0) X(11, 5, 10, 10, 200, 3, 8, 0) X(15, 8, 8, 10, 256, 2, 8, 0) \
-    X(19, 5, 1, 10, 80, 10, 8, 1) X(27, 5, 1, 10, RC_WNT(160, 80), RC_WNT(5, 8), 16, 2)
+    X(19, 5, 1, 10, 80, 10, 8, 1) X(27, 5, 1, 10, 160, 5, 16, 2)
 #define RC_V3_ALL(X) RC_V3_GROUP0(X) RC_V3_GROUP1(X) RC_V3_GROUP2(X) RC_V3_GROUP3(X)
 constexpr int kV3Groups = 4;
 
