@@ -9,7 +9,7 @@
 namespace rc {
 
 // ---- the functor kinds the register-radix kernels (rc_fft3.cuh) are compiled for ----
-enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2, kLdTma = 3, kLdAng = 4 };
+enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2, kLdTma = 3, kLdAng = 4, kLdGatherTma = 5 };
 enum { kStC64 = 0, kStLmr = 1, kStWin = 2, kStAng = 3 };
 
 struct LoadAny {
@@ -20,6 +20,7 @@ struct LoadAny {
     LoadDiscriminatorPacked disc;
     LoadAnglePacked angle;
     CUtensorMap tmap;          // host copy; handed to the kernel as its own __grid_constant__ argument
+    CUtensorMap tmap2;         // kLdGatherTma: the Hann-weight table (tmap describes the spectrum)
 };
 struct StoreAny {
     int kind;
@@ -58,7 +59,34 @@ inline LoadAny to_any(const LoadC64& l, const FftPass& P, int batch) {
 #endif
     return a;
 }
-inline LoadAny to_any(const LoadTunerGather& l, const FftPass&, int) { LoadAny a{}; a.kind = kLdGather; a.gather = l; return a; }
+// The tuner gather becomes two TMA boxes per tile when the geometry is regular: with R even the
+// first R/2 rows of a tile are positive-frequency bins and the last R/2 negative-frequency bins,
+// each an arithmetic progression of stride S = num/R in the spectrum.  The spectrum is described
+// as overlapping rows of S + T bins at stride S, so a box may start at any bin.  Tiles whose
+// progression wraps around the end of the spectrum use the per-thread path (decided per CTA).
+inline LoadAny to_any(const LoadTunerGather& l, const FftPass& P, int) {
+    LoadAny a{};
+    a.kind = kLdGather;
+    a.gather = l;
+#ifndef RC_EMULATE
+    static const bool no_tma = getenv("RC_NO_TMA") != nullptr || getenv("RC_NO_TMA_GATHER") != nullptr;
+    const long long S = P.stride;
+    if (!no_tma && P.R % 2 == 0 && P.R / 2 <= 256 && S % 4 == 0 && l.num == S * P.R && l.half == (long long)(P.R / 2) * S &&
+        l.n_x < (1LL << 30) && S + P.T < (1LL << 30)) {
+        const unsigned long long rows = (unsigned long long)((l.n_x + S - 1) / S);
+        const bool ok1 = tma_encode_2d_f32(&a.tmap, l.X, 2ULL * (unsigned long long)(S + P.T), rows, (unsigned long long)S * 8,
+                                           2u * (unsigned)P.T, (unsigned)(P.R / 2));
+        // weights: one box when the tile has <= 256 rows, else two halves (their shared-memory
+        // destinations must stay 128-byte aligned: R/2 rows of 4*T bytes)
+        const unsigned wrows = P.R <= 256 ? (unsigned)P.R : (unsigned)(P.R / 2);
+        const bool walign = P.R <= 256 || ((P.R / 2) * P.T * 4) % 128 == 0;
+        const bool ok2 = ok1 && walign && tma_encode_2d_f32(&a.tmap2, l.wtab, (unsigned long long)S, (unsigned long long)P.R,
+                                                            (unsigned long long)S * 4, (unsigned)P.T, wrows);
+        if (ok2) { a.kind = kLdGatherTma; a.box_rows = P.R / 2; }
+    }
+#endif
+    return a;
+}
 inline LoadAny to_any(const LoadDiscriminatorPacked& l, const FftPass&, int) { LoadAny a{}; a.kind = kLdDisc; a.disc = l; return a; }
 inline StoreAny to_any(const StoreC64& s) { StoreAny a{}; a.kind = kStC64; a.c64 = s; return a; }
 inline StoreAny to_any(const StoreLmrPacked& s) { StoreAny a{}; a.kind = kStLmr; a.lmr = s; return a; }

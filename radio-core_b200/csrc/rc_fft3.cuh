@@ -48,6 +48,8 @@ struct V3Sched {
     static constexpr int PITCH = (R % 2 == 0) ? R + 1 : R;   // float2 pitch of the transposed [column][K] layout (odd)
     static constexpr int TILE_F4 = R * CP_ + 2 * CP_;        // float4 slots: tile, and room for the transposed layout
     static constexpr int SMEM_BYTES = TILE_F4 * 16 + R * 8 + 16;   // + W_R table + mbarrier
+    static constexpr int WIN_OFF = (SMEM_BYTES + 127) / 128 * 128;  // tuner gather by TMA: + [R][T] Hann weights
+    static constexpr int SMEM_BYTES_WIN = WIN_OFF + R * T * 4;
     static_assert(CP_ == 8 || CP_ == 16, "8 or 16 column pairs");
     static_assert(NT_ % CP_ == 0, "threads must be a multiple of the column pairs");
     static_assert(T * PITCH <= TILE_F4 * 2, "transposed layout must fit the tile buffer");
@@ -73,6 +75,19 @@ template <int CP> struct V3FromTile {
     struct Ctx {};
     RC_HD Ctx prepare(int) const { return Ctx{}; }
     RC_HD float4 get(const Ctx&, int row, int cp, long long, bool) const { return tile[row * CP + cp]; }
+};
+// tile of raw spectrum bins staged by TMA next to a tile of their Hann weights (tuner gather)
+template <int CP> struct V3FromTileWin {
+    const float4* tile;
+    const float* win;          // [R][2*CP] weights
+    struct Ctx {};
+    RC_HD Ctx prepare(int) const { return Ctx{}; }
+    RC_HD float4 get(const Ctx&, int row, int cp, long long, bool) const {
+        const float4 x = tile[row * CP + cp];
+        const float2 w = *(const float2*)(win + row * 2 * CP + 2 * cp);
+        const float2 a = cscale(make_float2(x.x, x.y), w.x), d = cscale(make_float2(x.z, x.w), w.y);
+        return make_float4(a.x, a.y, d.x, d.y);
+    }
 };
 template <class LoadOp> struct V3FromOp {
     const LoadOp* ld;

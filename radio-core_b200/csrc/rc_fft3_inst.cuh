@@ -22,21 +22,71 @@ __device__ __forceinline__ void v3_issue_tile(float4* tile, uint64_t* bar, const
 // first pass of a plan: fused LoadOp (or TMA-staged complex64), column runs re-ordered through shared memory
 template <class S, int SIGN>
 __global__ void __launch_bounds__(S::NT, S::MINB_FIRST)
-v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __grid_constant__ CUtensorMap tmap) {
+v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __grid_constant__ CUtensorMap tmap,
+                const __grid_constant__ CUtensorMap tmap2) {
     extern __shared__ __align__(128) unsigned char rc_v3_smem[];
     float4* tile = (float4*)rc_v3_smem;
     float2* tw = (float2*)(rc_v3_smem + (size_t)S::TILE_F4 * 16);
     uint64_t* bar = (uint64_t*)(tw + S::R);
+    int* flag = (int*)(bar + 1);
+    float* win = (float*)(rc_v3_smem + S::WIN_OFF);           // gather by TMA only: [R][T] Hann weights
     const int batch = blockIdx.y + blockIdx.z * gridDim.y;
     const long long j0 = (long long)blockIdx.x * S::T;
     if (j0 >= P.stride) return;                    // padding CTA of the last cluster
     const int tid = threadIdx.x;
     const bool tma = ld.kind == kLdTma;
     if (tma && tid == 0) v3_issue_tile<S>(tile, bar, &tmap, ld.box_rows, j0, batch);
+    if (ld.kind == kLdGatherTma && tid == 0) {
+        // rows [0, R/2): bins (j0 + t*S - r) mod n;  rows [R/2, R): (j0 + t*S + n - num - r) mod n
+        const LoadTunerGather& gth = ld.gather;
+        const unsigned nx = (unsigned)gth.n_x, r = (unsigned)ldg(gth.roll + batch), Sd = (unsigned)P.stride;
+        unsigned sa = (unsigned)j0 + nx - r;
+        if (sa >= nx) sa -= nx;
+        unsigned sb = (unsigned)j0 + (unsigned)gth.half + (unsigned)(gth.n_x - gth.num) + nx - r;
+        if (sb >= nx) sb -= nx;
+        if (sb >= nx) sb -= nx;
+        const unsigned span = (unsigned)(S::R / 2 - 1) * Sd + (unsigned)S::T;
+        // no wrap-around inside either half, and box starts on 16-byte boundaries (even bins)
+        const int ok = (sa + span <= nx) && (sb + span <= nx) && (((sa | sb) & 1u) == 0u);
+        *flag = ok;
+        if (ok) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (uint32_t)(S::R * S::T * (sizeof(float2) + sizeof(float))));
+            tma_load_2d(tile, &tmap, bar, (int)(2u * (sa % Sd)), (int)(sa / Sd));
+            tma_load_2d(tile + (size_t)(S::R / 2) * S::CP, &tmap, bar, (int)(2u * (sb % Sd)), (int)(sb / Sd));
+            tma_load_2d(win, &tmap2, bar, (int)j0, 0);
+            if (S::R > 256) tma_load_2d(win + (size_t)(S::R / 2) * S::T, &tmap2, bar, (int)j0, S::R / 2);
+        }
+    }
     v3_load_table<S, SIGN>(tw, P, tid);
     const V3Tw tws = v3_twiddle_setup<S, false>(P, j0, tid);
     __syncthreads();
-    switch (ld.kind) {
+    int kind = ld.kind;
+    if (kind == kLdGatherTma) {
+        if (*flag) {
+            mbar_wait(bar, 0);
+            if (j0 == 0) {
+                // column 0 of row R/2 is bin num/2: the box delivered its merged partner X[n - num/2 - r]
+                if (tid == 0) {
+                    const LoadTunerGather& gth = ld.gather;
+                    const long long r = ldg(gth.roll + batch);
+                    long long sp = gth.half - r;
+                    if (sp < 0) sp += gth.n_x;
+                    const float2 xp = ldg(gth.X + sp);
+                    float2* e = (float2*)(tile + (size_t)(S::R / 2) * S::CP);
+                    const float ratio = gth.w_neg_half / win[(size_t)(S::R / 2) * S::T];
+                    *e = make_float2(xp.x + ratio * e->x, xp.y + ratio * e->y);
+                }
+                __syncthreads();
+            }
+            v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTileWin<S::CP>{tile, win}, batch, j0, tid, tws);
+            kind = -1;
+        } else {
+            kind = kLdGather;                      // this tile wraps around the spectrum: per-thread loads
+        }
+    }
+    switch (kind) {
+        case -1: break;
         case kLdTma:
             mbar_wait(bar, 0);
             v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTile<S::CP>{tile}, batch, j0, tid, tws);
@@ -158,11 +208,12 @@ cudaError_t v3_run_first(const FftPass& P, const LoadAny& ld, const StoreC64& st
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(v3_first_kernel<S, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(v3_first_kernel<S, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES_WIN);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    return v3_launch(v3_first_kernel<S, SIGN>, tiles, batch, S::NT, (size_t)S::SMEM_BYTES, stream, P, ld, st, ld.tmap);
+    const size_t smem = ld.kind == kLdGatherTma ? (size_t)S::SMEM_BYTES_WIN : (size_t)S::SMEM_BYTES;
+    return v3_launch(v3_first_kernel<S, SIGN>, tiles, batch, S::NT, smem, stream, P, ld, st, ld.tmap, ld.tmap2);
 #endif
 }
 

@@ -65,6 +65,21 @@ inline bool tma_encode_tile_map(CUtensorMap* map, const TileSource& s, int box_r
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+
+// rank-2 map over float32: dim0 contiguous, dim1 at `row_stride_bytes` (a multiple of 16)
+inline bool tma_encode_2d_f32(CUtensorMap* map, const void* base, unsigned long long dim0, unsigned long long dim1,
+                              unsigned long long row_stride_bytes, unsigned box0, unsigned box1) {
+    if (tma_encode_fn() == nullptr || ((uintptr_t)base % 16) != 0 || (row_stride_bytes % 16) != 0 || box0 > 256 || box1 > 256 ||
+        (box0 * 4) % 16 != 0) return false;
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t es[2] = {1u, 1u};
+    CUresult r = tma_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
 #endif
 
 #if defined(__CUDACC__) && !defined(RC_EMULATE)
@@ -87,6 +102,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");

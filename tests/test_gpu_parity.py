@@ -217,3 +217,83 @@ def test_fused_last_two_passes_gpu(rc, n, batch, monkeypatch):
         outs.append(out.cpu().numpy())
     assert lib.rc_fused_errors() == 0
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_fft_one_billion_points(rc):
+    """BASELINE config 5 size (N = 1e9 = 2^9 5^9, four passes): index arithmetic at the top of the
+    32-bit range.  Two complex exponentials -> two spectral lines of known height, everything else
+    at the fp32 noise floor."""
+    import torch
+    from radiocore import _native
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~40 GB of device memory")
+    n, k0, k1 = 1_000_000_000, 123_456_789, 999_999_937
+    t = torch.arange(n, device="cuda", dtype=torch.int64)
+    x = torch.empty(n, dtype=torch.complex64, device="cuda")
+    step = 50_000_000
+    for s in range(0, n, step):                      # build in slices: exact integer phase index, fp64 angle
+        tt = t[s:s + step]
+        ph0 = torch.remainder(tt * k0, n).to(torch.float64) * (2 * np.pi / n)
+        ph1 = torch.remainder(tt * k1, n).to(torch.float64) * (2 * np.pi / n)
+        x[s:s + step] = (torch.polar(torch.ones_like(ph0), ph0) + 0.5 * torch.polar(torch.ones_like(ph1), ph1)).to(torch.complex64)
+        del tt, ph0, ph1
+    del t
+    out = torch.empty_like(x)
+    _native.check(_native.lib().rc_fft_c2c(0, n, 1, -1, x.data_ptr(), out.data_ptr(), None))
+    torch.cuda.synchronize()
+    a0, a1 = out[k0].item(), out[k1].item()
+    assert abs(a0 - n) / n < 2e-5, a0
+    assert abs(a1 - 0.5 * n) / n < 2e-5, a1
+    out[k0] = 0
+    out[k1] = 0
+    mag = out.abs()
+    assert float(mag.max()) / n < 2e-5                # nothing leaked into other bins
+    assert float(mag.pow(2).sum().sqrt()) / n < 2e-5 * 3
+
+
+def test_example_server_loop(rc):
+    """examples/multi_fm_synthetic.py: the reference's multi_fm_server loop (RingBuffer -> Buffer ->
+    Tuner.load -> per-channel run -> tobytes) with stand-ins for the radio and the socket."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "multi_fm_synthetic.py")
+    spec = importlib.util.spec_from_file_location("multi_fm_synthetic", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    frames = mod.main(blocks=2)
+    assert len(frames) == 6
+    topics = [int.from_bytes(a, "little") for a, _ in frames[:3]]
+    assert topics == [int(f) for f, _, _ in mod.Config.channels]
+    assert [n for _, n in frames[:3]] == [48000 * 2 * 4, 48000 * 4, 48000 * 4]
+
+
+def test_config3_literal_block(rc):
+    """BASELINE config 3 as benchmarked: N = 256e6, 256 x 1 MHz channels, FM 1e6 -> 48e3 -- the engine
+    on the full block against the oracle on a subset of channels (ch 0, 1, 127, 255)."""
+    import torch
+    import bench
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~25 GB of device memory")
+    N, C_, B, A = 256_000_000, 256, 1_000_000, 48_000
+    x_dev, offs = bench.make_wideband_gpu(N, C_, B, 3, False, "cuda")
+    g = rc.Tuner(cuda=True)
+    for off in offs:
+        g.add_channel(100e6 + off, B, rc.FM(B, A, cuda=True))
+    g.request_bandwidth(N)
+    g.load(x_dev)
+    audio = g.run_all(numpy_output=True).copy()
+    slices = g.audio_slices()
+    x = x_dev.cpu().numpy()
+    del x_dev
+    torch.cuda.empty_cache()
+    o = oracle.Tuner(fft_workers=os.cpu_count())
+    for off in offs:
+        o.add_channel(100e6 + off, B, oracle.FM(B, A))
+    o.request_bandwidth(N)
+    o.load(x)
+    worst = 0.0
+    for c in (0, 1, 127, 255):
+        off_c, size, nch = slices[c]
+        got = audio[off_c: off_c + size * nch].reshape(size, nch)
+        ref = o.channels()[c].demodulator.run(o.run(c))
+        worst = max(worst, parity.assert_parity(got, ref, f"cfg3 literal ch{c}"))
+    print("config3 literal worst rel err", worst)
