@@ -9,7 +9,7 @@
 namespace rc {
 
 // ---- the functor kinds the register-radix kernels (rc_fft3.cuh) are compiled for ----
-enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2, kLdTma = 3, kLdAng = 4, kLdGatherTma = 5 };
+enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2, kLdTma = 3, kLdAng = 4, kLdGatherTma = 5, kLdAngTma = 6 };
 enum { kStC64 = 0, kStLmr = 1, kStWin = 2, kStAng = 3 };
 
 struct LoadAny {
@@ -90,7 +90,22 @@ inline LoadAny to_any(const LoadTunerGather& l, const FftPass& P, int) {
 inline LoadAny to_any(const LoadDiscriminatorPacked& l, const FftPass&, int) { LoadAny a{}; a.kind = kLdDisc; a.disc = l; return a; }
 inline StoreAny to_any(const StoreC64& s) { StoreAny a{}; a.kind = kStC64; a.c64 = s; return a; }
 inline StoreAny to_any(const StoreLmrPacked& s) { StoreAny a{}; a.kind = kStLmr; a.lmr = s; return a; }
-inline LoadAny to_any(const LoadAnglePacked& l, const FftPass&, int) { LoadAny a{}; a.kind = kLdAng; a.angle = l; return a; }
+// The angle samples of a packed column pair are 16 contiguous bytes: the tile is staged exactly
+// like a complex64 tile (two samples = one "complex" element).
+inline LoadAny to_any(const LoadAnglePacked& l, const FftPass& P, int batch) {
+    LoadAny a{};
+    a.kind = kLdAng;
+    a.angle = l;
+#ifndef RC_EMULATE
+    static const bool no_tma = getenv("RC_NO_TMA") != nullptr || getenv("RC_NO_TMA_ANGLE") != nullptr;
+    TileSource src{(const float2*)l.ang, P.stride, l.batch_stride / 2, P.stride, P.R, batch};
+    if (!no_tma && l.batch_stride % 2 == 0 && tma_source_ok(src)) {
+        const int br = tma_box_rows(P.R);
+        if (tma_encode_tile_map(&a.tmap, src, br, P.T)) { a.kind = kLdAngTma; a.box_rows = br; }
+    }
+#endif
+    return a;
+}
 inline StoreAny to_any(const StoreAngle& s) { StoreAny a{}; a.kind = kStAng; a.angle = s; return a; }
 inline StoreAny to_any(const StoreC64Win& s) { StoreAny a{}; a.kind = kStWin; a.win = s; return a; }
 

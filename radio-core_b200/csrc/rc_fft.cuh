@@ -759,6 +759,7 @@ inline bool fft_tuned_split(long long n, std::vector<int>& Rs) {
         {256000000LL, {640, 800, 500, 0}},
         {1000000LL, {200, 50, 100, 0}},
         {500000LL, {200, 50, 50, 0}},
+        {250000LL, {500, 500, 0, 0}},
     };
     for (const Row& row : rows)
         if (row.n == n) {

@@ -55,6 +55,14 @@ struct V3Sched {
     static_assert(T * PITCH <= TILE_F4 * 2, "transposed layout must fit the tile buffer");
 };
 
+RC_HD float wrap_half_turns_dev(float x) {      // (-2, 2) half-turns -> (-1, 1]   (= wrap_half_turns of rc_ops.cuh)
+#ifdef __CUDA_ARCH__
+    return x - 2.0f * rintf(0.5f * x);
+#else
+    return x - 2.0f * nearbyintf(0.5f * x);
+#endif
+}
+
 RC_HD float2 f4lo(float4 v) { return make_float2(v.x, v.y); }
 RC_HD float2 f4hi(float4 v) { return make_float2(v.z, v.w); }
 RC_HD float4 f4make(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
@@ -71,6 +79,7 @@ RC_HD void v3_load_table(float2* tw, const FftPass& P, int tid) {
 
 // Sources of stage 0: the tile already staged in shared memory (TMA), or a LoadOp functor.
 template <int CP> struct V3FromTile {
+    static constexpr bool kTile = true;         // staged tile: columns past the end hold zeros, every lane may read
     const float4* tile;
     struct Ctx {};
     RC_HD Ctx prepare(int) const { return Ctx{}; }
@@ -78,6 +87,7 @@ template <int CP> struct V3FromTile {
 };
 // tile of raw spectrum bins staged by TMA next to a tile of their Hann weights (tuner gather)
 template <int CP> struct V3FromTileWin {
+    static constexpr bool kTile = true;
     const float4* tile;
     const float* win;          // [R][2*CP] weights
     struct Ctx {};
@@ -89,7 +99,32 @@ template <int CP> struct V3FromTileWin {
         return make_float4(a.x, a.y, d.x, d.y);
     }
 };
+#if defined(__CUDACC__) && !defined(RC_EMULATE)
+// tile of angle(y)/pi samples staged by TMA (two samples per column): packed FM discriminator
+// d[n] = wrap(a[n] - a[n-1]) (LoadAnglePacked).  The sample before a column pair comes from the
+// neighbouring lane (same row), or from global memory for the first pair of the tile.
+template <int CP> struct V3FromTileAng {
+    static constexpr bool kTile = true;
+    const float4* tile;
+    const float* ang;          // this batch entry's samples
+    long long stride;          // packed columns per row
+    struct Ctx {};
+    __device__ Ctx prepare(int) const { return Ctx{}; }
+    __device__ float4 get(const Ctx&, int row, int cp, long long j, bool) const {
+        const float4 x = tile[row * CP + cp];
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned group = 0xFFu << (lane & 24u);                 // the 8 (or 2 x 8) lanes of this row group
+        float prev = __shfl_up_sync(CP == 8 ? group : (0xFFFFu << (lane & 16u)), x.w, 1, CP);
+        const long long i = j + (long long)row * stride;             // first packed element of the pair
+        if (cp == 0) prev = i > 0 ? __ldg(ang + 2 * i - 1) : x.x;
+        float d0 = wrap_half_turns_dev(x.x - prev);
+        if (i == 0) d0 = 0.f;
+        return make_float4(d0, wrap_half_turns_dev(x.y - x.x), wrap_half_turns_dev(x.z - x.y), wrap_half_turns_dev(x.w - x.z));
+    }
+};
+#endif
 template <class LoadOp> struct V3FromOp {
+    static constexpr bool kTile = false;
     const LoadOp* ld;
     long long stride;
     typedef typename LoadOp::Ctx Ctx;
@@ -153,7 +188,7 @@ RC_HD void v3_stage0(float4* tile, const float2* tw, const FftPass& P, const Src
         const int u = g + it * S::NG;
         if (S::NB0 % S::NG != 0 && u >= S::NB0) break;
         float2 a[S::R0], b[S::R0];
-        if (act_a) {
+        if (act_a || Src::kTile) {
 #pragma unroll
             for (int t0 = 0; t0 < S::R0; t0++) {
                 const float4 x = src.get(sctx, t0 * S::U + u, cp, j, act_b);

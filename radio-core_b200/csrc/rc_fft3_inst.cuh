@@ -34,7 +34,7 @@ v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __gr
     const long long j0 = (long long)blockIdx.x * S::T;
     if (j0 >= P.stride) return;                    // padding CTA of the last cluster
     const int tid = threadIdx.x;
-    const bool tma = ld.kind == kLdTma;
+    const bool tma = ld.kind == kLdTma || ld.kind == kLdAngTma;
     if (tma && tid == 0) v3_issue_tile<S>(tile, bar, &tmap, ld.box_rows, j0, batch);
     if (ld.kind == kLdGatherTma && tid == 0) {
         // rows [0, R/2): bins (j0 + t*S - r) mod n;  rows [R/2, R): (j0 + t*S + n - num - r) mod n
@@ -90,6 +90,11 @@ v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __gr
         case kLdTma:
             mbar_wait(bar, 0);
             v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTile<S::CP>{tile}, batch, j0, tid, tws);
+            break;
+        case kLdAngTma:
+            mbar_wait(bar, 0);
+            v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTileAng<S::CP>{tile, ld.angle.ang + batch * ld.angle.batch_stride, P.stride},
+                                      batch, j0, tid, tws);
             break;
         case kLdGather: v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadTunerGather>{&ld.gather, P.stride}, batch, j0, tid, tws); break;
         case kLdDisc: v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadDiscriminatorPacked>{&ld.disc, P.stride}, batch, j0, tid, tws); break;
