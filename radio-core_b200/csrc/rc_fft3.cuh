@@ -334,7 +334,7 @@ RC_HD void v3_last_first_a(const float4* tile, float4* hold, int tid) {
     for (int it = 0; it < S::IT2; it++) {
         const int q = g + it * S::NG;
         if (S::NB2 % S::NG != 0 && q >= S::NB2) break;
-        const int k1 = q % S::R1, k0 = q / S::R1;
+        const int k0 = q % S::R0, k1 = q / S::R0;      // k0 fastest: the row groups of a warp write consecutive K
         const int base = k0 * S::U + k1 * S::R2;
         float2 a[S::R2], b[S::R2];
 #pragma unroll
@@ -357,7 +357,7 @@ RC_HD void v3_last_first_b(float2* tr, const float4* hold, int tid) {
     for (int it = 0; it < S::IT2; it++) {
         const int q = g + it * S::NG;
         if (S::NB2 % S::NG != 0 && q >= S::NB2) break;
-        const int k1 = q % S::R1, k0 = q / S::R1;
+        const int k0 = q % S::R0, k1 = q / S::R0;      // k0 fastest: the row groups of a warp write consecutive K
         const int K0 = k0 + S::R0 * k1;
 #pragma unroll
         for (int k2 = 0; k2 < S::R2; k2++) {
