@@ -268,7 +268,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": what},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ B200 arm
@@ -440,11 +440,29 @@ def run_b200(args, rank, world, local_rank):
         except Exception as exc:       # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {exc!r}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the real stdout (see main: everything else a library
+    prints on fd 1 -- e.g. NCCL's version banner -- is diverted to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    global _JSON_FD
     args = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
