@@ -189,6 +189,7 @@ struct DemodBank {
     double* d_zi = nullptr; double* d_zi_next = nullptr;
     double* d_stage = nullptr; double* d_partial = nullptr;
     double* d_g = nullptr; int gK = 0;
+    std::vector<double> g_host;
     float2 *Z1 = nullptr, *Z2 = nullptr, *ZpB = nullptr, *ZpA = nullptr, *w0 = nullptr, *w1 = nullptr;
     float *mpx = nullptr, *pilot = nullptr, *lmr = nullptr, *audio_tmp = nullptr;
 
@@ -233,6 +234,7 @@ struct DemodBank {
             if (rc) return fail(rc, "wbfm: 19 kHz pilot filter needs input_size > 38100");
             std::vector<double> g = autocorr_taps(b);
             gK = 40;
+            g_host = g;
             RC_API_CUDA(arena.upload(&d_g, g), "pilot taps");
             RC_API_CUDA(arena.alloc(&Z2, (size_t)batch * h), "alloc Z2");
             RC_API_CUDA(arena.alloc(&ZpB, (size_t)batch * h), "alloc ZpB");
@@ -288,7 +290,8 @@ struct DemodBank {
             RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreC64{(float2*)mpx, h, 1.0f}, w0, w1, st,
                                   "wbfm.irfft_mpx")), "ifft mpx");
             // pilot = Bandpass(19 kHz +- 50, 41 taps).run(mpx)   (wbfm.py:45-46,80)
-            RC_API_CUDA(launch_filtfilt(FiltFiltEw{mpx, pilot, d_g, B, gK}, batch, st, "wbfm.pilot_filtfilt"), "pilot filtfilt");
+            RC_API_CUDA(launch_filtfilt(FiltFiltEw{mpx, pilot, d_g, B, gK}, batch, st, "wbfm.pilot_filtfilt", g_host.data()),
+                        "pilot filtfilt");
             // PLL.step (hilbert) + image(2) * mpx * 1.0175      (wbfm.py:80-83)
             RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadC64{(const float2*)pilot, h}, StoreC64{Z2, h, 1.0f}, w0, w1, st,
                                   "wbfm.rfft_pilot")), "fft pilot");
@@ -308,7 +311,7 @@ struct DemodBank {
         p.in = audio_tmp; p.out = out; p.zi = d_zi; p.zi_next = d_zi_next; p.taps = d_taps;
         p.stage = d_stage; p.partial = d_partial;
         p.A = A; p.nch = nch; p.ntaps = 51; p.deemph = 1; p.dc_clip = 1;
-        RC_API_CUDA(launch_epilogue(p, batch, st), "epilogue");
+        RC_API_CUDA(launch_epilogue(p, batch, st, taps), "epilogue");
         std::swap(d_zi, d_zi_next);
         return RC_OK;
     }
@@ -731,7 +734,7 @@ int rc_deemph_run(rc_deemph* d, const float* in, float* outp, void* stream) {
     p.in = in; p.out = outp; p.zi = d->d_zi; p.zi_next = d->d_zi_next; p.taps = d->d_taps;
     p.stage = nullptr; p.partial = nullptr;
     p.A = d->size; p.nch = 1; p.ntaps = 51; p.deemph = 1; p.dc_clip = 0;
-    RC_API_CUDA(launch_epilogue(p, 1, (cudaStream_t)stream), "deemph");
+    RC_API_CUDA(launch_epilogue(p, 1, (cudaStream_t)stream, d->taps), "deemph");
     std::swap(d->d_zi, d->d_zi_next);
     return RC_OK;
 }
@@ -742,6 +745,7 @@ struct rc_bandpass {
     long long size = 0;
     Arena arena;
     std::vector<float> taps;
+    std::vector<double> g_host;
     double* d_g = nullptr;
     int K = 0;
 };
@@ -755,6 +759,7 @@ int rc_bandpass_create(int device, int64_t size, double lo_hz, double hi_hz, int
     int rc = firwin_bandpass(num_taps, lo_hz / nyq, hi_hz / nyq, window ? window : "hamm", b->taps);
     if (rc) return fail(rc, "bandpass: invalid cutoff frequencies, tap count or window");
     std::vector<double> gt = autocorr_taps(b->taps);
+    b->g_host = gt;
     b->K = num_taps - 1;
     RC_API_CUDA(b->arena.upload(&b->d_g, gt), "taps");
     RC_API_CUDA(dev_sync(0), "sync");
@@ -777,7 +782,8 @@ int rc_bandpass_run(rc_bandpass* b, const float* in, float* outp, void* stream) 
     if (b->size <= 3 * (long long)b->taps.size())
         return fail(RC_ERR_INVALID, "The length of the input vector x must be greater than padlen");
     DeviceGuard g(b->device);
-    RC_API_CUDA(launch_filtfilt(FiltFiltEw{in, outp, b->d_g, b->size, b->K}, 1, (cudaStream_t)stream), "filtfilt");
+    RC_API_CUDA(launch_filtfilt(FiltFiltEw{in, outp, b->d_g, b->size, b->K}, 1, (cudaStream_t)stream, "filtfilt", b->g_host.data()),
+                "filtfilt");
     return RC_OK;
 }
 

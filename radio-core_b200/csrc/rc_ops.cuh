@@ -670,6 +670,34 @@ __device__ __forceinline__ void fir_window8_t(const double* xs, const double* ta
         for (int i = 0; i < 8; i++) w[i] = w[8 + i];
     }
 }
+// Taps handed to the kernel by value: after full unrolling every tap is a constant-bank operand of
+// its DFMA, so the inner loop is 64 DFMA per 8 shared-memory loads (the shared-memory tap table of
+// the generic path costs one more load per 8 DFMA and makes the loop LSU-bound).
+struct FirTapsParam {
+    double t[88];
+    int n8;                    // 0: not provided (use the device tap table)
+};
+template <int NT8>
+__device__ __forceinline__ void fir_window8_c(const double* xs, const FirTapsParam& tp, int o, double acc[kFirPer]) {
+    double w[16];
+    const double* x0 = xs + fir_slot(o);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = x0[i];
+#pragma unroll
+    for (int j0 = 0; j0 < NT8; j0 += 8) {
+        const double* x1 = xs + fir_slot(o + j0 + 8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[8 + i] = x1[i];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+#pragma unroll
+            for (int r = 0; r < kFirPer; r++) acc[r] = fma(tp.t[j0 + jj], w[r + jj], acc[r]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = w[8 + i];
+    }
+}
+
 __device__ __forceinline__ void fir_window8(const double* xs, const double* taps, int ntaps8, int o, double acc[kFirPer]) {
     if (ntaps8 == 88) fir_window8_t<88>(xs, taps, ntaps8, o, acc);          // 81-tap pilot filter (41 (*) 41)
     else if (ntaps8 == 56) fir_window8_t<56>(xs, taps, ntaps8, o, acc);     // 51-tap de-emphasis
@@ -677,7 +705,8 @@ __device__ __forceinline__ void fir_window8(const double* xs, const double* taps
 }
 
 // Phase 1 of the audio epilogue: de-emphasis FIR of one chunk, fp64 staging, per-chunk sum.
-static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const EpilogueParams p, int nchunks) {
+static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const EpilogueParams p, int nchunks,
+                                                                     const __grid_constant__ FirTapsParam ctaps) {
     __shared__ double xs[kFirSlots];
     __shared__ double tp[kFirMaxTaps];
     __shared__ double red[kFirThreads / 32];
@@ -702,7 +731,8 @@ static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const Epilo
 #pragma unroll
     for (int r = 0; r < kFirPer; r++) acc[r] = 0.0;
     const int o = tid * kFirPer;
-    fir_window8(xs, tp, ntaps8, o, acc);
+    if (ctaps.n8 == 56 && ntaps8 == 56) fir_window8_c<56>(xs, ctaps, o, acc);
+    else fir_window8(xs, tp, ntaps8, o, acc);
     double sum = 0.0;
 #pragma unroll
     for (int r = 0; r < kFirPer; r++) {
@@ -754,7 +784,7 @@ static __global__ void __launch_bounds__(256) epi_finish_kernel(const EpiloguePa
 }
 
 // Zero-phase FIR (FiltFiltEw) with shared-memory staging of the odd-extended input.
-static __global__ void __launch_bounds__(kFirThreads) filtfilt_kernel(const FiltFiltEw f) {
+static __global__ void __launch_bounds__(kFirThreads) filtfilt_kernel(const FiltFiltEw f, const __grid_constant__ FirTapsParam ctaps) {
     __shared__ double xs[kFirSlots];
     __shared__ double tp[kFirMaxTaps];
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -771,7 +801,8 @@ static __global__ void __launch_bounds__(kFirThreads) filtfilt_kernel(const Filt
 #pragma unroll
     for (int r = 0; r < kFirPer; r++) acc[r] = 0.0;
     const int o = tid * kFirPer;
-    fir_window8(xs, tp, ntaps8, o, acc);
+    if (ctaps.n8 == 88 && ntaps8 == 88) fir_window8_c<88>(xs, ctaps, o, acc);
+    else fir_window8(xs, tp, ntaps8, o, acc);
 #pragma unroll
     for (int r = 0; r < kFirPer; r++) {
         const long long n = n0 + o + r;
@@ -782,7 +813,8 @@ static __global__ void __launch_bounds__(kFirThreads) filtfilt_kernel(const Filt
 
 inline int epi_chunks(long long A) { return (int)((A + kFirChunk - 1) / kFirChunk); }
 
-inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStream_t stream) {
+// taps_host: the same ntaps float taps on the host (optional; enables the constant-operand FIR loop)
+inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStream_t stream, const float* taps_host = nullptr) {
 #ifdef RC_EMULATE
     const long long total = p.A * p.nch;
     for (int b = 0; b < batch; b++) {
@@ -805,7 +837,14 @@ inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStrea
     const int nchunks = epi_chunks(p.A);
     {
         ProfileScope scope("demod.deemph_fir", (4.0 + (p.dc_clip ? 8.0 : 4.0)) * (double)p.A * p.nch * batch, stream);
-        epi_fir_kernel<<<dim3((unsigned)nchunks, (unsigned)(batch * p.nch)), kFirThreads, 0, stream>>>(p, nchunks);
+        FirTapsParam ct;
+        memset(&ct, 0, sizeof(ct));
+        if (taps_host && p.deemph && p.ntaps > 48 && p.ntaps <= 56) {
+            const int K = p.ntaps - 1;
+            for (int i = 0; i <= K; i++) ct.t[i] = (double)taps_host[K - i];      // reversed, as in the kernel's table
+            ct.n8 = 56;
+        }
+        epi_fir_kernel<<<dim3((unsigned)nchunks, (unsigned)(batch * p.nch)), kFirThreads, 0, stream>>>(p, nchunks, ct);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -819,14 +858,23 @@ inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStrea
 #endif
 }
 
-inline cudaError_t launch_filtfilt(const FiltFiltEw& f, int batch, cudaStream_t stream, const char* tag = "filtfilt") {
+// g_host: the 2K+1 taps on the host (optional; enables the constant-operand FIR loop)
+inline cudaError_t launch_filtfilt(const FiltFiltEw& f, int batch, cudaStream_t stream, const char* tag = "filtfilt",
+                                   const double* g_host = nullptr) {
 #ifdef RC_EMULATE
     return launch_ew(f.n, batch, f, stream);
 #else
     if (batch <= 0 || f.n <= 0) return cudaSuccess;
     if (2 * f.K + 1 > kFirMaxTaps - 8) return launch_ew(f.n, batch, f, stream, tag, 8.0 * (double)f.n * batch);
     ProfileScope scope(tag, 8.0 * (double)f.n * batch, stream);
-    filtfilt_kernel<<<dim3((unsigned)((f.n + kFirChunk - 1) / kFirChunk), (unsigned)batch), kFirThreads, 0, stream>>>(f);
+    FirTapsParam ct;
+    memset(&ct, 0, sizeof(ct));
+    const int ntaps = 2 * f.K + 1;
+    if (g_host && ntaps > 80 && ntaps <= 88) {
+        for (int i = 0; i < ntaps; i++) ct.t[i] = g_host[i];
+        ct.n8 = 88;
+    }
+    filtfilt_kernel<<<dim3((unsigned)((f.n + kFirChunk - 1) / kFirChunk), (unsigned)batch), kFirThreads, 0, stream>>>(f, ct);
     return cudaGetLastError();
 #endif
 }
