@@ -50,6 +50,7 @@ struct V3Sched {
     static constexpr int SMEM_BYTES = TILE_F4 * 16 + R * 8 + 16;   // + W_R table + mbarrier
     static constexpr int WIN_OFF = (SMEM_BYTES + 127) / 128 * 128;  // tuner gather by TMA: + [R][T] Hann weights
     static constexpr int SMEM_BYTES_WIN = WIN_OFF + R * T * 4;
+    static constexpr int SMEM_BYTES_ANG = WIN_OFF + R * 4;          // angle tile by TMA: + one preceding sample per row
     static_assert(CP_ == 8 || CP_ == 16, "8 or 16 column pairs");
     static_assert(NT_ % CP_ == 0, "threads must be a multiple of the column pairs");
     static_assert(T * PITCH <= TILE_F4 * 2, "transposed layout must fit the tile buffer");
@@ -102,23 +103,21 @@ template <int CP> struct V3FromTileWin {
 #if defined(__CUDACC__) && !defined(RC_EMULATE)
 // tile of angle(y)/pi samples staged by TMA (two samples per column): packed FM discriminator
 // d[n] = wrap(a[n] - a[n-1]) (LoadAnglePacked).  The sample before a column pair comes from the
-// neighbouring lane (same row), or from global memory for the first pair of the tile.
+// neighbouring lane (same row); the one before a row's first pair was fetched into `before`
+// while the tile was in flight (a[-1] := a[0], so that d[0] = 0).
 template <int CP> struct V3FromTileAng {
     static constexpr bool kTile = true;
     const float4* tile;
-    const float* ang;          // this batch entry's samples
-    long long stride;          // packed columns per row
+    const float* before;       // shared: the sample preceding each row's first column (v3_first_kernel)
     struct Ctx {};
     __device__ Ctx prepare(int) const { return Ctx{}; }
-    __device__ float4 get(const Ctx&, int row, int cp, long long j, bool) const {
+    __device__ float4 get(const Ctx&, int row, int cp, long long, bool) const {
         const float4 x = tile[row * CP + cp];
         const unsigned lane = threadIdx.x & 31u;
         const unsigned group = 0xFFu << (lane & 24u);                 // the 8 (or 2 x 8) lanes of this row group
         float prev = __shfl_up_sync(CP == 8 ? group : (0xFFFFu << (lane & 16u)), x.w, 1, CP);
-        const long long i = j + (long long)row * stride;             // first packed element of the pair
-        if (cp == 0) prev = i > 0 ? __ldg(ang + 2 * i - 1) : x.x;
-        float d0 = wrap_half_turns_dev(x.x - prev);
-        if (i == 0) d0 = 0.f;
+        if (cp == 0) prev = before[row];
+        const float d0 = wrap_half_turns_dev(x.x - prev);
         return make_float4(d0, wrap_half_turns_dev(x.y - x.x), wrap_half_turns_dev(x.z - x.y), wrap_half_turns_dev(x.w - x.z));
     }
 };

@@ -29,7 +29,7 @@ v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __gr
     float2* tw = (float2*)(rc_v3_smem + (size_t)S::TILE_F4 * 16);
     uint64_t* bar = (uint64_t*)(tw + S::R);
     int* flag = (int*)(bar + 1);
-    float* win = (float*)(rc_v3_smem + S::WIN_OFF);           // gather by TMA only: [R][T] Hann weights
+    float* win = (float*)(rc_v3_smem + S::WIN_OFF);           // gather by TMA: [R][T] Hann weights; angle by TMA: [R] samples
     const int batch = blockIdx.y + blockIdx.z * gridDim.y;
     const long long j0 = (long long)blockIdx.x * S::T;
     if (j0 >= P.stride) return;                    // padding CTA of the last cluster
@@ -56,6 +56,15 @@ v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __gr
             tma_load_2d(tile + (size_t)(S::R / 2) * S::CP, &tmap, bar, (int)(2u * (sb % Sd)), (int)(sb / Sd));
             tma_load_2d(win, &tmap2, bar, (int)j0, 0);
             if (S::R > 256) tma_load_2d(win + (size_t)(S::R / 2) * S::T, &tmap2, bar, (int)j0, S::R / 2);
+        }
+    }
+    if (ld.kind == kLdAngTma) {
+        // the sample before each row's first column lies in the neighbouring tile: fetch the R of
+        // them now, behind the TMA load, instead of one dependent load per row inside stage 0
+        const float* a = ld.angle.ang + batch * ld.angle.batch_stride;
+        for (int r = tid; r < S::R; r += S::NT) {
+            const long long i = 2 * (j0 + (long long)r * P.stride);
+            win[r] = ldg(a + (i > 0 ? i - 1 : 0));
         }
     }
     v3_load_table<S, SIGN>(tw, P, tid);
@@ -93,7 +102,7 @@ v3_first_kernel(const FftPass P, const LoadAny ld, const StoreC64 st, const __gr
             break;
         case kLdAngTma:
             mbar_wait(bar, 0);
-            v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTileAng<S::CP>{tile, ld.angle.ang + batch * ld.angle.batch_stride, P.stride},
+            v3_stage0<S, SIGN, false>(tile, tw, P, V3FromTileAng<S::CP>{tile, win},
                                       batch, j0, tid, tws);
             break;
         case kLdGather: v3_stage0<S, SIGN, false>(tile, tw, P, V3FromOp<LoadTunerGather>{&ld.gather, P.stride}, batch, j0, tid, tws); break;
@@ -217,7 +226,8 @@ cudaError_t v3_run_first(const FftPass& P, const LoadAny& ld, const StoreC64& st
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    const size_t smem = ld.kind == kLdGatherTma ? (size_t)S::SMEM_BYTES_WIN : (size_t)S::SMEM_BYTES;
+    const size_t smem = ld.kind == kLdGatherTma ? (size_t)S::SMEM_BYTES_WIN
+                      : ld.kind == kLdAngTma  ? (size_t)S::SMEM_BYTES_ANG : (size_t)S::SMEM_BYTES;
     return v3_launch(v3_first_kernel<S, SIGN>, tiles, batch, S::NT, smem, stream, P, ld, st, ld.tmap, ld.tmap2);
 #endif
 }
