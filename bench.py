@@ -51,6 +51,9 @@ WORKLOADS = {
              "configs[1]: Tuner 10 MHz -> 32 x 250 kHz + MFM (N=10e6, C=32, B=250e3, A=48e3)"),
     "cfg4": (16_000_000, 64, 250_000, 48_000, "WBFM",
              "configs[3]: 64-channel WBFM stereo with de-emphasis (N=16e6, C=64, B=250e3, A=48e3)"),
+    "cfg5": (1_000_000_000, 2048, 250_000, 48_000, "FM",
+             "configs[4]: 1 Gsps wideband block, 2048 x 250 kHz FM channels (256 per GPU at 8 GPUs), "
+             "use with --gpus 8 --mode bcast (N=1e9, C=2048, B=250e3, A=48e3)"),
     "small": (4_000_000, 16, 250_000, 48_000, "MFM", "smoke-sized: N=4e6, C=16, B=250e3, MFM"),
 }
 
@@ -288,10 +291,14 @@ def run_b200(args, rank, world, local_rank):
 
     from radiocore.tools import sharding
     tuner = radiocore.Tuner(cuda=True)
+    feed = None
     if bcast:
-        # one wideband stream, replicated: rank 0 generates, one NCCL broadcast per block,
+        # one wideband stream, replicated: rank 0 generates, one NCCL broadcast per block
+        # (posted one block ahead, so it overlaps the kernels of the previous block),
         # every rank demodulates its contiguous slice of the channels
-        x_dev, offs = make_wideband_gpu(N, Cn, B, 3, kind == "WBFM", device)
+        offs = tiling_offsets(N, Cn, B)
+        x_dev = make_wideband_gpu(N, Cn, B, 3, kind == "WBFM", device)[0] if rank == 0 else None
+        feed = sharding.BlockBroadcaster(N, device, src=0)
         my = sharding.shard_tuner(tuner, [100e6 + o for o in offs], B, lambda c: getattr(radiocore, kind)(B, A, cuda=True),
                                   100e6, N, world, rank)
     else:
@@ -308,10 +315,14 @@ def run_b200(args, rank, world, local_rank):
 
     def step_device():
         if bcast:
-            sharding.broadcast_block(x_dev, src=0)
-        tuner.load(x_dev)
+            feed.post(x_dev)                       # block k+1 starts travelling ...
+            tuner.load(feed.take())                # ... while block k is demodulated
+        else:
+            tuner.load(x_dev)
         tuner.run_all()
 
+    if bcast:
+        feed.post(x_dev)                           # prime: one block ahead
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
@@ -342,7 +353,52 @@ def run_b200(args, rank, world, local_rank):
     # Tuner.submit()/collect() is the package's block pipeline: the H2D copy of block k+1 runs
     # while block k is in the kernels and block k-1's audio is read back (depth 2).
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and bcast:
+        # one host stream: rank 0 copies each pinned block to the device on a side stream and
+        # broadcasts it from there; every rank demodulates its channel slice and reads its audio
+        # back.  Block k+1's copy and broadcast are queued before block k's kernels.
+        copy_stream = torch.cuda.Stream()
+        stage = [torch.empty(N, dtype=torch.complex64, device=device) for _ in range(3)] if rank == 0 else None
+        x_host = [torch.empty(N, dtype=torch.complex64).pin_memory() for _ in range(2)] if rank == 0 else None
+        if rank == 0:
+            for xh in x_host:
+                xh.copy_(x_dev)
+        torch.cuda.synchronize()
+        slices = tuner.audio_slices()
+        d2h = 4 * sum(size * nchn for _, size, nchn in slices)
+        state = {"i": 0}
+
+        def send_next():
+            i = state["i"]
+            state["i"] += 1
+            if rank != 0:
+                feed.post(None)
+                return
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_stream(torch.cuda.current_stream())    # the slot's previous reader is queued there
+                stage[i % 3].copy_(x_host[i % 2], non_blocking=True)
+                feed.post(stage[i % 3])                                  # ordered behind the copy, not behind the kernels
+
+        def run_e2e(steps):
+            checksum = 0.0
+            for _ in range(steps):
+                send_next()
+                tuner.load(feed.take())
+                checksum += float(tuner.run_all(numpy_output=True)[0])
+            return checksum
+
+        while feed.in_flight():                     # the device-resident leg leaves one block posted
+            feed.take()
+        send_next()
+        run_e2e(3)
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(args.steps)
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        feed.take()
+        e2e = {"t": t_e2e, "h2d": 8 * N, "d2h": d2h}
+    elif not args.no_e2e:
         x_host = [torch.empty(N, dtype=torch.complex64).pin_memory() for _ in range(2)]
         for xh in x_host:
             xh.copy_(x_dev)
@@ -370,6 +426,9 @@ def run_b200(args, rank, world, local_rank):
         e2e = {"t": t_e2e, "h2d": 8 * N, "d2h": d2h}
 
     # ---- reduce over ranks (max time)
+    if bcast:
+        while feed.in_flight():                     # nothing left travelling when the ranks part
+            feed.take()
     t_dev = torch.tensor([ms_total, (e2e["t"] if e2e else 0.0)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -427,10 +486,13 @@ def run_b200(args, rank, world, local_rank):
                               "note": "SURVEY 8(d) bytes (read IQ once + write audio) over the whole step"},
             "kernels": table, "clocks": clocks}
     if e2e:
+        api = ("rank 0: pinned host IQ -> H2D -> BlockBroadcaster (NCCL, one block ahead); every rank: Tuner.load + run_all "
+               "-> D2H of its channels' audio") if bcast else \
+            "Tuner.submit()/collect(): pinned host IQ -> H2D -> kernels -> D2H of all channels' audio, 2 blocks in flight"
         line["e2e"] = {"value": samples_per_step * args.steps / t_e2e / 1e6, "unit": UNIT,
-                       "h2d_bytes_per_step": e2e["h2d"] * streams, "d2h_bytes_per_step": e2e["d2h"] * streams,
+                       "h2d_bytes_per_step": e2e["h2d"] * streams, "d2h_bytes_per_step": e2e["d2h"] * world,
                        "ms_per_step": t_e2e / args.steps * 1e3, "timing": "wall clock between device synchronisations, max over ranks",
-                       "api": "Tuner.submit()/collect(): pinned host IQ -> H2D -> kernels -> D2H of all channels' audio, 2 blocks in flight"}
+                       "api": api}
     if world == 1 and not args.no_cpu_baseline:
         try:
             workers = host_workers(N, limit=None)

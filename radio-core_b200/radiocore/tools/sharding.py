@@ -8,7 +8,8 @@ stream.  There is no reduction and no gather of audio: every rank emits its own 
 
 Works on any ``torch.distributed`` backend (NCCL on the GPUs, gloo in the CPU tests).
 """
-from typing import List, Sequence
+import collections
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -58,3 +59,59 @@ def broadcast_block(block: torch.Tensor, src: int = 0) -> torch.Tensor:
         return block
     dist.broadcast(torch.view_as_real(block) if block.is_complex() else block, src=src)
     return block
+
+
+class BlockBroadcaster:
+    """Double-buffered broadcast of the wideband block: block k+1 travels while block k is in
+    the kernels.
+
+    ``post()`` starts the (asynchronous) broadcast of the next block, ``take()`` returns the
+    oldest posted block once it has arrived -- on NCCL "arrived" is a stream dependency, the host
+    does not block.  The source rank sends straight from the tensor it passes to ``post`` (no
+    staging copy; it must leave that tensor alone until the block has been taken); the other
+    ranks receive into ``depth`` rotating device buffers, so a buffer is only overwritten after
+    the work queued on it ``depth`` posts earlier, which the collective is ordered behind.
+    Every rank must call post/take in the same order.  With one rank it degenerates to a queue.
+    """
+
+    def __init__(self, n_samples: int, device, src: int = 0, depth: int = 2):
+        if depth < 2:
+            raise ValueError("depth must be at least 2")
+        self._src = int(src)
+        self._world = dist.get_world_size() if dist.is_initialized() else 1
+        self._rank = dist.get_rank() if dist.is_initialized() else 0
+        self._is_src = self._world == 1 or self._rank == self._src
+        self._n = int(n_samples)
+        self._slots = [] if self._is_src else [torch.empty(self._n, dtype=torch.complex64, device=device)
+                                                for _ in range(depth)]
+        self._depth = depth
+        self._turn = 0
+        self._pending = collections.deque()
+
+    def post(self, block: Optional[torch.Tensor] = None) -> None:
+        """Start sending (source rank: ``block`` required) / receiving the next block."""
+        if len(self._pending) >= self._depth:
+            raise RuntimeError("too many blocks in flight: take() before the next post()")
+        if self._is_src:
+            if block is None or block.numel() != self._n or block.dtype != torch.complex64:
+                raise ValueError("the source rank posts a complex64 block of the configured size")
+            buf = block
+        else:
+            buf = self._slots[self._turn]
+            self._turn = (self._turn + 1) % self._depth
+        work = None
+        if self._world > 1:
+            work = dist.broadcast(torch.view_as_real(buf), src=self._src, async_op=True)
+        self._pending.append((buf, work))
+
+    def take(self) -> torch.Tensor:
+        """Oldest posted block, ordered after its arrival."""
+        if not self._pending:
+            raise RuntimeError("take() without a posted block")
+        buf, work = self._pending.popleft()
+        if work is not None:
+            work.wait()
+        return buf
+
+    def in_flight(self) -> int:
+        return len(self._pending)

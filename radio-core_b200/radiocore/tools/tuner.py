@@ -229,6 +229,8 @@ class Tuner:
         lib = _native.lib()
         src = input_signal if isinstance(input_signal, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(np.asarray(input_signal), dtype=np.complex64))
+        if src.is_cuda:                                   # produced by work queued on the caller's stream
+            p["copy"].wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(p["copy"]):
             if p["ev_loaded"][slot] is not None:          # the slot's previous block has been transformed
                 p["copy"].wait_event(p["ev_loaded"][slot])

@@ -36,14 +36,24 @@ def _worker(rank, world, port, out_dir):
         mine = sharding.shard_tuner(tuner, centers, B, lambda c: oracle.MFM(B, A), F0, N, world, rank)
         assert mine == list(sharding.channel_slice(C_, world, rank))
         audio = {}
+        # block 0 through the plain broadcast, block 1 through the double-buffered feed
+        # (posted one block ahead, as bench.py --mode bcast does on the GPUs)
+        block = torch.zeros(N, dtype=torch.complex64)
+        if rank == 0:
+            block = torch.from_numpy(synth.wideband(N, offs, B, seed=5, block=0))
+        sharding.broadcast_block(block, src=0)
+        feed = sharding.BlockBroadcaster(N, "cpu", src=0)
+        nxt = torch.from_numpy(synth.wideband(N, offs, B, seed=5, block=1)) if rank == 0 else None
+        feed.post(nxt)
         for blk in range(2):
-            block = torch.zeros(N, dtype=torch.complex64)
-            if rank == 0:
-                block = torch.from_numpy(synth.wideband(N, offs, B, seed=5, block=blk))
-            sharding.broadcast_block(block, src=0)
+            if blk == 1:
+                block = feed.take()
+                assert feed.in_flight() == 0
             tuner.load(block.numpy())
             for ch in tuner.channels():
                 audio[(blk, mine[ch.index])] = ch.demodulator.run(tuner.run(ch.index))
+        with pytest.raises(RuntimeError):
+            feed.take()
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), audio, allow_pickle=True)
         # no reduction, no gather on the data path: only a barrier to end together
         dist.barrier()
