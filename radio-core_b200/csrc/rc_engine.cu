@@ -624,6 +624,7 @@ int rc_decimate_run_real(rc_decimate* d, const float* in, float* outp, void* str
             size_t w = (size_t)(d->n_in > d->n_out ? d->n_in : d->n_out);
             RC_API_CUDA(d->arena.alloc(&d->ow0, w), "alloc");
             RC_API_CUDA(d->arena.alloc(&d->ow1, w), "alloc");
+            RC_API_CUDA(dev_sync(0), "sync");
             d->odd_ready = true;
         }
         RC_API_CUDA((fft_exec<-1>(d->planI, 1, LoadRealAsComplex{in, d->n_in}, StoreC64{d->Xr, d->n_in, 1.0f},
@@ -911,6 +912,7 @@ int rc_fft_c2c(int device, int64_t n, int batch, int sign, const void* in, void*
     float2 *w0 = nullptr, *w1 = nullptr;
     RC_API_CUDA(arena.alloc(&w0, (size_t)n * batch), "alloc");
     RC_API_CUDA(arena.alloc(&w1, (size_t)n * batch), "alloc");
+    RC_API_CUDA(dev_sync(0), "table sync");     // twiddle tables were uploaded on the default stream
     cudaError_t e;
     if (sign < 0) e = fft_exec<-1>(plan, batch, LoadC64{(const float2*)in, n}, StoreC64{(float2*)outp, n, 1.0f}, w0, w1, st);
     else e = fft_exec<+1>(plan, batch, LoadC64{(const float2*)in, n}, StoreC64{(float2*)outp, n, 1.0f}, w0, w1, st);
