@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """The per-block loop of the reference's examples/multi_fm_server.py:86-106,123-136 against this
-package, with the radio and the ZeroMQ socket replaced by stand-ins (no SoapySDR / pyzmq here):
+package.  The radio is replaced by a stand-in (no SoapySDR here); the egress is the reference's:
+a ZeroMQ PUB socket, one multipart message per channel and block,
+``[int32-LE centre frequency, float32 audio bytes]``, decoded by subscribers exactly as
+examples/multi_fm_receiver.py:23-24,47-49 does (falls back to a frame recorder without pyzmq).
 
     SDR thread  -> RingBuffer -> DSP thread: Tuner.load, per channel Tuner.run + demodulator.run
-                                            -> "socket.send_multipart([address_bytes, audio.tobytes()])"
+                                            -> socket.send_multipart([address_bytes, audio.tobytes()])
 
 Run:  python examples/multi_fm_synthetic.py [blocks]
 """
@@ -30,14 +33,46 @@ class Config:
     deemphasis = 75e-6
 
 
-class FakeSocket:
-    """Stands in for the ZeroMQ PUB socket: collects the multipart frames."""
+try:
+    import zmq
+except ImportError:                                           # pragma: no cover
+    zmq = None
 
-    def __init__(self):
-        self.frames = []
+
+class RecordingSocket:
+    """Wraps the PUB socket (or nothing, without pyzmq) and keeps (topic, payload size) of every frame."""
+
+    def __init__(self, socket=None):
+        self.frames, self.socket = [], socket
 
     def send_multipart(self, parts):
         self.frames.append((bytes(parts[0]), len(parts[1])))
+        if self.socket is not None:
+            self.socket.send_multipart(parts)
+
+
+class Receiver(threading.Thread):
+    """examples/multi_fm_receiver.py without the sound card: subscribe to one station by its
+    address bytes, decode each payload as float32 and reshape to (samples, channels)."""
+
+    def __init__(self, context, endpoint, frequency, channels, blocks):
+        super().__init__(daemon=True)
+        self.socket = context.socket(zmq.SUB)
+        self.socket.connect(endpoint)
+        self.socket.setsockopt(zmq.SUBSCRIBE, int(frequency).to_bytes(4, byteorder="little"))
+        self.socket.setsockopt(zmq.RCVTIMEO, 60_000)
+        self.channels, self.blocks, self.audio = channels, blocks, []
+
+    def run(self):
+        try:
+            for _ in range(self.blocks):
+                _, payload = self.socket.recv_multipart()
+                audio = np.frombuffer(payload, dtype=np.float32)
+                self.audio.append(audio.reshape((len(audio) // self.channels, self.channels)))
+        except zmq.Again:                                     # publisher died: leave what arrived
+            pass
+        finally:
+            self.socket.close(0)
 
 
 def sdr_thread(ring, blocks, offsets):
@@ -64,7 +99,18 @@ def main(blocks=2):
     producer = threading.Thread(target=sdr_thread, args=(ring, blocks, offsets), daemon=True)
     producer.start()
 
-    socket = FakeSocket()
+    context = pub = None
+    receivers = []
+    if zmq is not None:
+        context = zmq.Context()
+        pub = context.socket(zmq.PUB)
+        port = pub.bind_to_random_port("tcp://127.0.0.1")
+        for channel in tuner.channels():
+            receivers.append(Receiver(context, f"tcp://127.0.0.1:{port}", channel.center_frequency,
+                                      channel.demodulator.channels, blocks))
+            receivers[-1].start()
+        time.sleep(0.3)                               # PUB/SUB: let the subscriptions reach the publisher
+    socket = RecordingSocket(pub)
     tmp_buffer = Buffer(cfg.input_rate, cuda=True)
     done = 0
     while done < blocks:
@@ -77,6 +123,13 @@ def main(blocks=2):
             socket.send_multipart([channel.address_bytes, tmp.tobytes()])
         done += 1
     producer.join()
+    main.received = []
+    if zmq is not None:
+        for r in receivers:
+            r.join(30)
+            main.received.append(r.audio)
+        pub.close(0)
+        context.term()
     return socket.frames
 
 
@@ -84,3 +137,5 @@ if __name__ == "__main__":
     frames = main(int(sys.argv[1]) if len(sys.argv) > 1 else 2)
     for addr, nbytes in frames:
         print("topic", int.from_bytes(addr, "little"), "Hz ->", nbytes, "bytes of float32 audio")
+    for (freq, _, kind), blocks_rx in zip(Config.channels, main.received):
+        print("subscriber", int(freq), kind, "received", [a.shape for a in blocks_rx])

@@ -264,6 +264,12 @@ def test_example_server_loop(rc):
     topics = [int.from_bytes(a, "little") for a, _ in frames[:3]]
     assert topics == [int(f) for f, _, _ in mod.Config.channels]
     assert [n for _, n in frames[:3]] == [48000 * 2 * 4, 48000 * 4, 48000 * 4]
+    if mod.zmq is not None:
+        # every subscriber got both blocks of its own station, decoded as the reference's receiver does
+        shapes = [[a.shape for a in rx] for rx in mod.main.received]
+        assert shapes == [[(48000, 2)] * 2, [(48000, 1)] * 2, [(48000, 1)] * 2]
+        for rx in mod.main.received:
+            assert all(np.all(np.isfinite(a)) and np.max(np.abs(a)) <= 0.999 + 1e-6 for a in rx)
 
 
 def test_config3_literal_block(rc):

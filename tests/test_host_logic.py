@@ -100,3 +100,43 @@ def test_ringbuffer_and_buffer_plumbing():
     with b.consume() as a:
         a[:] = 1
     assert b.data.sum() == 8 and len(b) == 8
+
+
+def test_wire_format_round_trip():
+    """Egress of the server loop (multi_fm_server.py:103-106): topic = Channel.address_bytes
+    (int32-LE centre frequency), payload = float32 audio bytes; the receiver
+    (multi_fm_receiver.py:23-24,47-49) subscribes by that prefix and reshapes to (samples, channels)."""
+    zmq = pytest.importorskip("zmq")
+    import time
+    import radiocore
+    tuner = radiocore.Tuner()
+    for f in (96.9e6, 94.5e6):
+        tuner.add_channel(f, 240e3, None)
+    want = tuner.channels()[1]
+    assert want.address_bytes == int(94.5e6).to_bytes(4, byteorder="little")
+    ctx = zmq.Context()
+    pub, sub = ctx.socket(zmq.PUB), ctx.socket(zmq.SUB)
+    try:
+        port = pub.bind_to_random_port("tcp://127.0.0.1")
+        sub.connect(f"tcp://127.0.0.1:{port}")
+        sub.setsockopt(zmq.SUBSCRIBE, int(94.5e6).to_bytes(4, byteorder="little"))
+        sub.setsockopt(zmq.RCVTIMEO, 5000)
+        stereo = np.random.default_rng(0).uniform(-1, 1, (1, 480, 2)).astype(np.float32)   # WBFM.run's shape
+        for _ in range(50):                      # slow joiner: publish until the subscription is live
+            for ch in tuner.channels():
+                pub.send_multipart([ch.address_bytes, stereo.tobytes()])
+            try:
+                topic, payload = sub.recv_multipart(flags=zmq.NOBLOCK)
+                break
+            except zmq.Again:
+                time.sleep(0.05)
+        else:
+            pytest.fail("no frame received")
+        assert topic == want.address_bytes      # only the subscribed station arrives
+        audio = np.frombuffer(payload, dtype=np.float32)
+        audio = audio.reshape((len(audio) // 2, 2))
+        assert np.array_equal(audio, stereo[0])
+    finally:
+        pub.close(0)
+        sub.close(0)
+        ctx.term()
