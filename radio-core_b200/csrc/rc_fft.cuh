@@ -693,7 +693,7 @@ inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long lon
     X(17, 10, 10, 10, 400, 1, 8, 0) X(21, 8, 1, 10, 80, 10, 8, 1) X(33, 8, 1, 10, 160, 5, 16, 2)
 #define RC_V3_GROUP2(X) \
     X(2, 5, 5, 5, 200, 4, 8, 0) X(6, 5, 5, 10, 200, 4, 8, 0) X(10, 5, 8, 10, 320, 2, 8, 0) X(14, 5, 5, 25, 200, 2, 8, 0) \
-    X(18, 5, 1, 8, 64, 10, 8, 1) X(30, 5, 1, 8, 128, 8, 16, 2)
+    X(18, 5, 1, 8, 64, 10, 8, 1) X(30, 5, 1, 8, 128, 8, 16, 2) X(34, 5, 1, 10, 160, 5, 32, 2)
 #define RC_V3_GROUP3(X) \
     X(3, 10, 1, 15, 128, 4, 8, 0) X(7, 4, 8, 8, 256, 4, 8, 0) X(11, 5, 10, 10, 200, 3, 8, 0) X(15, 8, 8, 10, 256, 2, 8, 0) \
     X(19, 5, 1, 10, 80, 10, 8, 1) X(27, 5, 1, 10, 160, 5, 16, 2)
@@ -719,10 +719,23 @@ inline const std::vector<V3Entry>& v3_table() {
     return t;
 }
 // schedule of length R usable as the first (first = true) or as a later pass of a plan
+// 64-column variants (cp = 32: 512-byte rows, one warp per row) are preferred for later passes
+// unless the fused pair kernel, which is compiled for 32-column tiles, was asked for.
+inline bool v3_wide64() {
+    static const bool on = getenv("RC_FUSE") == nullptr && getenv("RC_NO_WIDE64") == nullptr;
+    return on;
+}
 inline const V3Entry* v3_find(int R, bool first) {
-    for (const V3Entry& e : v3_table())
-        if (e.R() == R && (e.role == 0 || e.role == (first ? 1 : 2))) return &e;
-    return nullptr;
+    const V3Entry* hit = nullptr;
+    for (const V3Entry& e : v3_table()) {
+        if (e.R() != R || !(e.role == 0 || e.role == (first ? 1 : 2))) continue;
+        if (e.cp == 32) {
+            if (v3_wide64()) return &e;
+            continue;
+        }
+        if (!hit) hit = &e;
+    }
+    return hit;
 }
 inline bool v3_has(int R) { return v3_find(R, true) && v3_find(R, false); }
 

@@ -32,11 +32,13 @@
 namespace rc {
 
 // CP = column pairs per tile: 8 (16 columns, 128-byte rows) or, for short passes whose tiles
-// stay small, 16 (32 columns, 256-byte rows: a whole DRAM segment per row).
+// stay small, 16 (32 columns, 256-byte rows: a whole DRAM segment per row) or 32 (64 columns:
+// one warp per row; R = 50, whose last stage has only 5 butterflies per column pair and would
+// leave half of 10 row groups idle at 32 columns).
 template <int R0_, int R1_, int R2_, int NT_, int MINB_, int CP_ = 8>
 struct V3Sched {
     static constexpr int R0 = R0_, R1 = R1_, R2 = R2_, NT = NT_, MINB = MINB_;
-    static constexpr int CP = CP_, T = 2 * CP_, LOGCP = CP_ == 8 ? 3 : 4;
+    static constexpr int CP = CP_, T = 2 * CP_, LOGCP = CP_ == 8 ? 3 : (CP_ == 16 ? 4 : 5);
     static constexpr int R = R0_ * R1_ * R2_;
     static constexpr int U = R1_ * R2_;
     static constexpr int NG = NT_ / CP_;                     // row groups working in parallel
@@ -51,7 +53,7 @@ struct V3Sched {
     static constexpr int WIN_OFF = (SMEM_BYTES + 127) / 128 * 128;  // tuner gather by TMA: + [R][T] Hann weights
     static constexpr int SMEM_BYTES_WIN = WIN_OFF + R * T * 4;
     static constexpr int SMEM_BYTES_ANG = WIN_OFF + R * 4;          // angle tile by TMA: + one preceding sample per row
-    static_assert(CP_ == 8 || CP_ == 16, "8 or 16 column pairs");
+    static_assert(CP_ == 8 || CP_ == 16 || CP_ == 32, "8, 16 or 32 column pairs");
     static_assert(NT_ % CP_ == 0, "threads must be a multiple of the column pairs");
     static_assert(T * PITCH <= TILE_F4 * 2, "transposed layout must fit the tile buffer");
 };

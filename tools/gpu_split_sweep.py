@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Time alternative pass splits of the FFT plans (RC_FFT_SPLIT) on the GPU with the library's
+per-kernel event profiler:  python tools/gpu_split_sweep.py
+Each line: n, batch, split, per-pass ms, total ms.  Plain complex64 in/out (no fused loaders)."""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "radio-core_b200"))
+import torch  # noqa: E402
+from radiocore import _native  # noqa: E402
+
+lib = _native.lib()
+CASES = {
+    (256_000_000, 1): ["640x800x500", "400x800x800", "800x400x800", "640x625x640", "625x640x640", "500x800x640",
+                       "640x500x800", "512x625x800", "800x800x400"],
+    (1_000_000, 256): ["200x50x100", "200x100x50", "100x100x100", "160x125x50", "250x40x100", "125x80x100"],
+    (500_000, 256): ["200x50x50", "250x40x50", "125x80x50", "100x100x50", "100x50x100"],
+}
+
+
+def run(n, batch, split, reps=5):
+    os.environ["RC_FFT_SPLIT"] = f"{n}:{split}"
+    x = torch.randn(batch * n, 2, device="cuda")                 # interleaved complex64
+    out = torch.empty_like(x)
+    for _ in range(2):
+        _native.check(lib.rc_fft_c2c(0, n, batch, -1, x.data_ptr(), out.data_ptr(), None))
+    lib.rc_profile_reset()
+    lib.rc_profile_enable(1)
+    for _ in range(reps):
+        _native.check(lib.rc_fft_c2c(0, n, batch, -1, x.data_ptr(), out.data_ptr(), None))
+    need = lib.rc_profile_report(None, 0)
+    buf = C.create_string_buffer(need + 16)
+    lib.rc_profile_report(buf, need + 16)
+    lib.rc_profile_enable(0)
+    lib.rc_profile_reset()
+    k = json.loads(buf.value.decode())
+    per = {t: v["total_ms"] / v["count"] for t, v in k.items()}
+    return per
+
+
+for (n, batch), splits in CASES.items():
+    for s in splits:
+        try:
+            per = run(n, batch, s)
+            print(n, batch, s, " ".join(f"{t.split('/')[-1]}={v:.4f}" for t, v in per.items()), "total=%.4f" % sum(per.values()), flush=True)
+        except Exception as exc:
+            print(n, batch, s, "failed:", exc, flush=True)
