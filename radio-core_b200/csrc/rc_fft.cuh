@@ -721,9 +721,8 @@ inline const std::vector<V3Entry>& v3_table() {
 // schedule of length R usable as the first (first = true) or as a later pass of a plan
 // 64-column variants (cp = 32: 512-byte rows, one warp per row) are preferred for later passes
 // unless the fused pair kernel, which is compiled for 32-column tiles, was asked for.
-inline bool v3_wide64() {
-    static const bool on = getenv("RC_FUSE") == nullptr && getenv("RC_NO_WIDE64") == nullptr;
-    return on;
+inline bool v3_wide64() {       // read at plan build, not cached: the tests toggle RC_FUSE
+    return getenv("RC_FUSE") == nullptr && getenv("RC_NO_WIDE64") == nullptr;
 }
 inline const V3Entry* v3_find(int R, bool first) {
     const V3Entry* hit = nullptr;

@@ -119,3 +119,17 @@ def test_fused_last_two_passes_replay(emu, n, batch, monkeypatch):
     assert np.array_equal(plain, fused)
     ref = np.fft.fft(x.astype(np.complex128), axis=1)
     assert np.max(np.abs(fused - ref)) / np.sqrt(np.mean(np.abs(ref) ** 2)) < 3e-6
+
+
+def test_wide_tile_schedules_replay(emu, monkeypatch):
+    """The 64-column schedule of the R = 50 later pass (500 000 = 200 x 50 x 50, ragged last tile:
+    2500 columns are not a multiple of 64) against the 32-column one and against numpy."""
+    n = 500_000
+    rng = np.random.default_rng(64)
+    x = (rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))).astype(np.complex64)
+    wide = emu.fft(x, +1)
+    monkeypatch.setenv("RC_NO_WIDE64", "1")
+    narrow = emu.fft(x, +1)
+    assert np.array_equal(wide, narrow)               # same arithmetic, different tiling
+    ref = np.fft.ifft(x.astype(np.complex128), axis=1) * n
+    assert np.max(np.abs(wide - ref)) / np.sqrt(np.mean(np.abs(ref) ** 2)) < 3e-6
