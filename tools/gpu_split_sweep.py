@@ -14,17 +14,18 @@ from radiocore import _native  # noqa: E402
 
 lib = _native.lib()
 CASES = {
-    (256_000_000, 1): ["640x800x500", "640x500x800"],
-    (1_000_000, 256): ["200x50x100", "200x100x50", "100x100x100", "100x50x200", "200x50x50x2"],
-    (500_000, 256): ["200x50x50", "100x100x50", "100x50x100"],
-    (250_000, 32): ["500x500", "100x50x50", "50x100x50", "50x50x100", "625x400", "125x40x50", "250x1000"],
-    (125_000, 32): ["250x500", "50x50x50", "200x625", "625x200", "125x1000"],
-    (125_000, 128): ["250x500", "50x50x50", "200x625"],
-    (10_000_000, 1): ["200x100x500", "200x500x100", "250x200x200", "200x250x200", "100x400x250", "500x200x100",
-                      "160x250x250", "100x100x1000", "200x50x1000", "100x50x50x40"],
-    (16_000_000, 1): ["200x100x800", "200x200x400", "250x256x250", "256x250x250", "320x500x100", "640x250x100",
-                      "640x100x250", "200x400x200", "160x100x1000"],
+    (256_000_000, 1): ["640x800x500", "800x500x640", "800x640x500", "640x800x500", "800x500x640", "800x800x400"],
 }
+if len(sys.argv) > 1 and sys.argv[1] == "all":
+    CASES.update({
+        (256_000_000, 1): ["640x800x500", "640x500x800", "800x500x640", "400x800x800", "640x625x640", "512x625x800"],
+        (1_000_000, 256): ["200x50x100", "200x100x50", "100x100x100", "100x50x200"],
+        (500_000, 256): ["200x50x50", "100x100x50", "100x50x100"],
+        (250_000, 32): ["500x500", "100x50x50", "50x100x50", "50x50x100", "625x400", "125x40x50", "250x1000"],
+        (125_000, 32): ["250x500", "50x50x50", "200x625", "625x200", "125x1000"],
+        (10_000_000, 1): ["200x100x500", "200x500x100", "250x200x200", "200x250x200", "160x250x250"],
+        (16_000_000, 1): ["200x100x800", "200x200x400", "250x256x250", "256x250x250", "320x500x100"],
+    })
 
 
 def run(n, batch, split, reps=5):
