@@ -1,65 +1,80 @@
-"""Fixed-size sample buffer (mirror of radiocore/tools/buffer.py:10-93).
+"""Fixed-size sample buffer with the interface of the reference's ``Buffer``
+(radiocore/tools/buffer.py:10-93): ``data``, ``size``, ``dtype``, ``is_cuda``, ``is_locked``,
+``consume()``.
 
-Host plumbing only: a pinned NumPy-visible array (so ``Tuner.load`` can DMA it
-straight to the GPU) with the reference's optional mutex and ``consume()``.
+Host plumbing only.  Where the reference asks cuSignal for CUDA managed memory, this keeps a
+page-locked host array (when a GPU is present and ``cuda=True``), which is what ``Tuner.load`` /
+``Tuner.submit`` can DMA from at full PCIe rate; the NumPy view handed out is the same memory.
 """
 import threading
-from contextlib import contextmanager
 from typing import Union
 
 import numpy as np
 
 
+def _page_locked(array):
+    """(owner, view): a pinned copy of ``array`` if a CUDA device is usable, else the array itself."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pinned = torch.from_numpy(array).pin_memory()
+            return pinned, pinned.numpy()
+    except Exception:                      # no torch / no driver: plain pageable memory still works
+        pass
+    return None, array
+
+
+class _Lease:
+    """Context manager handing out the array, holding the buffer's mutex if it has one."""
+
+    def __init__(self, array, guard):
+        self._array, self._guard = array, guard
+
+    def __enter__(self):
+        if self._guard is not None:
+            self._guard.acquire()
+        return self._array
+
+    def __exit__(self, *exc):
+        if self._guard is not None:
+            self._guard.release()
+        return False
+
+
 class Buffer:
     def __init__(self, size: Union[int, float], dtype: str = "complex64", lock: bool = False,
                  cuda: bool = False):
-        self._lock = lock
-        self._cuda = cuda
-        self._size = int(size)
-        if self._lock:
-            self._mtx = threading.Lock()
-        self._pinned = None
-        self._buffer = np.zeros(self._size, dtype=dtype)
-        if cuda:
-            try:
-                import torch
-                if torch.cuda.is_available():
-                    t = torch.from_numpy(self._buffer).pin_memory()
-                    self._pinned, self._buffer = t, t.numpy()
-            except Exception:
-                pass
+        self._cuda = bool(cuda)
+        self._guard = threading.Lock() if lock else None
+        storage = np.zeros(int(size), dtype=dtype)
+        self._owner, self._array = _page_locked(storage) if self._cuda else (None, storage)
+
+    def __len__(self) -> int:
+        return self._array.shape[0]
+
+    @property
+    def size(self) -> int:
+        return len(self)
 
     @property
     def dtype(self):
-        return self._buffer.dtype
+        return self._array.dtype
 
     @property
     def is_cuda(self) -> bool:
         return self._cuda
 
     @property
-    def size(self) -> int:
-        return self._size
-
-    def __len__(self) -> int:
-        return self.size
-
-    @property
     def is_locked(self) -> bool:
-        if not self._lock:
+        if self._guard is None:
             raise ValueError("locking is not enabled in this instance")
-        return self._mtx.locked()
+        return self._guard.locked()
 
     @property
     def data(self):
-        return self._buffer
+        """The underlying array (no locking)."""
+        return self._array
 
-    @contextmanager
     def consume(self):
-        try:
-            if self._lock:
-                self._mtx.acquire()
-            yield self._buffer
-        finally:
-            if self._lock:
-                self._mtx.release()
+        """``with buffer.consume() as array:`` -- exclusive while inside when ``lock=True``."""
+        return _Lease(self._array, self._guard)

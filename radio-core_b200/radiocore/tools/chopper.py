@@ -1,17 +1,23 @@
-"""Fixed-size slicer (mirror of radiocore/tools/chopper.py:4-55); host plumbing."""
+"""Fixed-size slicer with the interface of the reference's ``Chopper``
+(radiocore/tools/chopper.py:4-55): views of consecutive chunks of a larger array; host plumbing."""
+from typing import Union
 
 
 class Chopper:
-    """Iterate over consecutive ``chunk_size`` slices of a ``size``-long buffer."""
+    def __init__(self, size: Union[int, float], chunk_size: Union[int, float]):
+        self._total, self._step = int(size), int(chunk_size)
+        if self._step <= 0 or self._total % self._step:
+            raise ValueError(f"cannot evenly divide array by chunk size ({self._total}, {self._step})")
 
-    def __init__(self, size, chunk_size):
-        self._size = int(size)
-        self._chunk = int(chunk_size)
-        if self._chunk <= 0 or self._size % self._chunk:
-            raise ValueError("size must be a positive multiple of chunk_size")
+    @property
+    def size(self) -> int:
+        return self._total
 
-    def chop(self, buffer):
-        if len(buffer) != self._size:
-            raise ValueError("buffer size mismatch")
-        for start in range(0, self._size, self._chunk):
-            yield buffer[start:start + self._chunk]
+    @property
+    def chunk_size(self) -> int:
+        return self._step
+
+    def chop(self, input_arr):
+        """Yield ``size // chunk_size`` consecutive views (no copies) of ``input_arr``."""
+        for begin in range(0, self._total, self._step):
+            yield input_arr[begin:begin + self._step]

@@ -23,6 +23,14 @@ class RingBuffer:
         self._guard = threading.Lock()
         self._event = threading.Event()
 
+    def __str__(self) -> str:
+        return str(self._buffer)
+
+    @property
+    def data(self):
+        """The backing array (oldest sample at the read position, not at index 0)."""
+        return self._buffer
+
     @property
     def dtype(self):
         return self._buffer.dtype
@@ -62,10 +70,10 @@ class RingBuffer:
         if n > self._capacity:
             raise ValueError("input buffer is larger than the ring capacity")
         if self.vacancy < n:
+            if not self._allow_overflow:
+                raise ValueError("Overflow happened.")
             if self._print_overflow:
                 print("overflow")
-            if not self._allow_overflow:
-                return False
             self.reset()
         first = min(n, self._capacity - self._tail)
         self._buffer[self._tail:self._tail + first] = arr[:first]

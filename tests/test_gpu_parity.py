@@ -333,3 +333,34 @@ def test_unaligned_device_inputs(rc):
     a = rc.FM(B, A, cuda=True).run(iq)
     b = rc.FM(B, A, cuda=True).run(big2[1:])
     assert np.array_equal(a, b)
+
+
+def test_reference_benchmark_call_pattern(rc):
+    """tests/benchmark.py of the reference, call for call (one iteration each): demodulators fed a
+    zero-filled ``Buffer.data``, ``Decimate`` on 10 M and 2.5 M complex samples, a ``Tuner`` whose
+    channels carry the demodulator *class* (never invoked) -- sizes and argument types as there."""
+    buff = rc.Buffer(int(256e3), dtype=np.complex64, cuda=True)
+    assert buff.data.dtype == np.complex64 and len(buff) == 256000
+    for cls, shape in ((rc.WBFM, (1, 32000, 2)), (rc.MFM, (32000, 1)), (rc.FM, (32000, 1))):
+        out = cls(256e3, 32e3, cuda=True).run(buff.data)
+        assert out.shape == shape and out.dtype == np.float32
+        if cls is not rc.WBFM:                      # WBFM on silence is 0/0 in the reference as well
+            assert np.all(np.isfinite(out))
+    for n_in in (10e6, 2.5e6):
+        big = rc.Buffer(n_in, dtype=np.complex64, cuda=True)
+        y = rc.Decimate(n_in, 250e3, cuda=True).run(big.data)
+        assert len(y) == 250000 and y.is_cuda and not bool(y.any())      # backend array, as the reference's cuda path
+    tuner = rc.Tuner(cuda=True)
+    for f in (94.5e6, 97.5e6, 96.9e6):
+        tuner.add_channel(f, int(250e3), rc.FM)
+    tuner.request_bandwidth(int(10e6))
+    block = rc.Buffer(10e6, dtype=np.complex64, cuda=True)
+    block.data[:] = synth.wideband(10_000_000, [f - tuner.input_frequency for f in (94.5e6, 97.5e6, 96.9e6)],
+                                   250_000, seed=8)
+    o = oracle.Tuner()
+    for f in (94.5e6, 97.5e6, 96.9e6):
+        o.add_channel(f, int(250e3), None)
+    o.request_bandwidth(int(10e6))
+    o.load(block.data)
+    tuner.load(block.data)
+    parity.assert_parity(np.asarray(tuner.run(0)), o.run(0), "benchmark tuner channel 0")

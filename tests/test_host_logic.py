@@ -140,3 +140,41 @@ def test_wire_format_round_trip():
         pub.close(0)
         sub.close(0)
         ctx.term()
+
+
+def test_carrousel_chopper_semantics():
+    """Behaviour the reference's tests/test_carrousel.py pins: a full ring overwrites its oldest item
+    and counts the overflow; Buffer items are handed out through their own consume()."""
+    import radiocore
+    ring = radiocore.Carrousel([[0], [0], [0]], print_overflow=False)
+    assert ring.is_empty and not ring.is_healthy and ring.capacity == 3
+    for v in (1, 2, 3, 4):
+        with ring.enqueue() as item:
+            item[0] = v
+    assert ring.is_full and ring.occupancy == 3 and ring.overflow == 1
+    got = []
+    while not ring.is_empty:
+        with ring.dequeue() as item:
+            got.append(item[0])
+    assert got == [2, 3, 4]
+    with pytest.raises(ValueError):
+        ring.dequeue()
+    bufs = radiocore.Carrousel([radiocore.Buffer(4, dtype="float32", lock=True) for _ in range(2)])
+    with bufs.enqueue() as arr:
+        assert bufs._items[0].is_locked
+        arr[:] = 7
+    assert not bufs._items[0].is_locked
+    with bufs.dequeue() as arr:
+        assert np.all(arr == 7)
+    chop = radiocore.Chopper(12, 4)
+    data = np.arange(12)
+    parts = list(chop.chop(data))
+    assert [p.tolist() for p in parts] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11]] and parts[0].base is data
+    assert (chop.size, chop.chunk_size) == (12, 4)
+    with pytest.raises(ValueError):
+        radiocore.Chopper(10, 4)
+    ringbuf = radiocore.RingBuffer(8, dtype=np.float32, allow_overflow=False)
+    ringbuf.put([1, 2, 3, 4, 5, 6])
+    with pytest.raises(ValueError):
+        ringbuf.put([7, 8, 9])
+    assert np.allclose(ringbuf.data[:6], [1, 2, 3, 4, 5, 6])
