@@ -107,10 +107,6 @@ int rc_pll_destroy(rc_pll* p);
 int rc_pll_step(rc_pll* p, const float* in_dev, void* stream);
 int rc_pll_eval(rc_pll* p, double mult, int imag, float* out_dev, void* stream);
 
-/* ---- health: non-zero if a fused FFT-pass kernel abandoned a dependency wait since the last
- *      call (its outputs are then invalid); clears the flag.  Host-mapped word: no sync.   */
-int rc_fused_errors(void);
-
 /* ---- per-kernel timing for bench.py: CUDA events around every launch ------ */
 int rc_profile_enable(int on);
 int rc_profile_reset(void);

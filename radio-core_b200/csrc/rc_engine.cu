@@ -378,7 +378,9 @@ int rc_engine_add_channel(rc_engine* e, int64_t roll, int64_t B, int64_t A, int 
     if (e->committed) return fail(RC_ERR_STATE, "engine: add_channel after commit");
     if (mode < 0 || mode > RC_MODE_NONE) return fail(RC_ERR_INVALID, "engine: unknown mode");
     if (mode == RC_MODE_NONE) A = 2;
-    if (B < 2 || B >= e->N) return fail(RC_ERR_INVALID, "engine: channel bandwidth must be in [2, n_input)");
+    // B == n_input (a single channel as wide as the block): resample with num == Nx keeps every bin
+    // and merges nothing (SciPy _signaltools.py:3861-3875), i.e. window multiply + inverse FFT
+    if (B < 2 || B > e->N) return fail(RC_ERR_INVALID, "engine: channel bandwidth must be in [2, n_input]");
     if (roll <= -e->N || roll >= e->N) return fail(RC_ERR_INVALID, "engine: |roll| must be < n_input");
     if ((B & 1) || (A & 1) || !fft_size_supported(B) || !fft_size_supported(A))
         return fail(RC_ERR_UNSUPPORTED, "engine: channel sizes must be even and factor into 2^a 3^b 5^c");
@@ -406,7 +408,7 @@ int rc_engine_commit(rc_engine* e) {
             float* d = nullptr;
             RC_API_CUDA(e->arena.upload(&d, tuner_window_table(e->N, c.B, &wn)), "window table");
             e->wtab[c.B] = d;
-            e->wneg[c.B] = wn;
+            e->wneg[c.B] = c.B == e->N ? 0.f : wn;      // num == Nx: bins +-num/2 coincide, nothing is merged
         }
         if ((size_t)c.B > maxB) maxB = (size_t)c.B;
         if (c.mode == RC_MODE_NONE) continue;
@@ -839,17 +841,6 @@ int rc_pll_eval(rc_pll* p, double mult, int imag, float* outp, void* stream) {
     DeviceGuard g(p->device);
     RC_API_CUDA(launch_ew(p->n, 1, PllEvalEw{p->z, outp, p->n, (float)mult, imag}, (cudaStream_t)stream), "pll eval");
     return RC_OK;
-}
-
-// Non-zero when a fused-pass kernel gave up waiting for a dependency (results of that call are
-// invalid); cleared by the call.  Never expected: the tile queue is ordered so that every
-// dependency is issued first.
-int rc_fused_errors(void) {
-    int* w = fused_error_word(false);
-    if (!w) return 0;
-    const int v = *w;
-    *w = 0;
-    return v;
 }
 
 // ------------------------------------------------------------------ profiling

@@ -137,74 +137,6 @@ inline cudaError_t v3_later(const FftPass& P, int sign, const LoadAny& ld, const
     }
 }
 
-// Geometry of a fused (pass A, pass B) pair -- see rc_fused.cuh for the scheme.
-struct FusedPair {
-    FftPass PA, PB;
-    int W, TA, TB;             // chunk width in columns; tile widths of the two schedules
-    int cpb;                   // chunks per batch entry = ceil(NsA / W)
-    long long nchunks;         // batch * cpb
-    int nA, nB;                // tiles per chunk: RB * W/TA, RA * W/TB
-    int lag, nslot;
-    float2* ring;              // nslot slots of RA*RB*W elements, layout [tB][K_A][W]
-    long long slot_elems;
-    int* doneA;                // [nchunks] tiles of pass A finished
-    int* doneB;                // [nchunks] tiles of pass B that have read their input
-    int* err;
-    int box_rows;              // TMA box rows over the ring (divides RB)
-    RC_HD long long total() const { return nchunks * (long long)(nA + nB); }
-};
-// defined in rc_fused_g0.cu
-cudaError_t v3_fused_dispatch(int id_a, int id_b, int sign, const FusedPair& f, const LoadAny& ld_a, const StoreAny& st_b,
-                              cudaStream_t stream);
-
-// Error word of the fused kernels (a dependency wait that ran out of budget): host-mapped, so the
-// host can poll it without synchronising (rc_fused_errors()).
-inline int* fused_error_word(bool device_view) {
-    static int* host = nullptr;
-    static int* dev = nullptr;
-    if (!host) {
-#ifdef RC_EMULATE
-        host = dev = (int*)calloc(1, sizeof(int));
-#else
-        if (cudaHostAlloc((void**)&host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
-            *host = 0;
-            if (cudaHostGetDevicePointer((void**)&dev, host, 0) != cudaSuccess) dev = nullptr;
-        } else {
-            host = nullptr;
-        }
-#endif
-    }
-    return device_view ? dev : host;
-}
-
-// Fill the pair for `batch` transforms; (re)allocates the chunk counters when the batch grows.
-inline cudaError_t fused_prepare(const FftPlan& plan, int batch, FusedPair& f) {
-    const FftPass& PA = plan.fast[plan.nfast - 2];
-    const FftPass& PB = plan.fast[plan.nfast - 1];
-    FftPlan::Fuse& fz = plan.fuse;
-    f.PA = PA; f.PB = PB;
-    f.W = fz.W; f.TA = PA.T; f.TB = PB.T;
-    f.cpb = (int)((PA.Ns + f.W - 1) / f.W);
-    f.nchunks = (long long)batch * f.cpb;
-    f.nA = PB.R * (f.W / f.TA);
-    f.nB = PA.R * (f.W / f.TB);
-    f.nslot = fz.nslot;
-    f.lag = fz.lag < f.nchunks ? fz.lag : (int)f.nchunks;
-    f.ring = fz.ring; f.slot_elems = fz.slot_elems;
-    f.box_rows = tma_box_rows(PB.R);
-    if (fz.cap < f.nchunks) {
-        cudaError_t err = cudaSuccess;
-        fz.counters = (int*)plan.store->alloc(sizeof(int) * (size_t)(2 * f.nchunks + 4), &err);
-        if (err != cudaSuccess || !fz.counters) return err != cudaSuccess ? err : cudaErrorMemoryAllocation;
-        fz.cap = f.nchunks;
-    }
-    f.err = fused_error_word(true);
-    if (!f.err) f.err = fz.counters;             // no mapped memory: keep the flag on the device
-    f.doneA = fz.counters + 4;
-    f.doneB = f.doneA + f.nchunks;
-    return cudaSuccess;
-}
-
 inline bool fft_grid_dims(int batch, int& by, int& bz) {
     by = batch; bz = 1;
     while (by > 65535) { bz *= 2; by = (batch + bz - 1) / bz; }
@@ -260,27 +192,9 @@ cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const Sto
     const int npass = fast ? plan.nfast : plan.npass;
     const FftPass* passes = fast ? plan.fast : plan.pass;
     const double plain = 8.0 * (double)plan.n * (double)batch;
-    // the last two passes as one kernel with an L2-resident intermediate (rc_fused.cuh)
-    bool fuse = false;
-    if constexpr (v3ok) fuse = fast && plan.fuse.ok && plan.fast[npass - 2].T <= plan.fuse.W && plan.fast[npass - 1].T <= plan.fuse.W;
     for (int i = 0; i < npass; i++) {
         const FftPass& P = passes[i];
         const bool first = i == 0, last = i == npass - 1;
-        if (fuse && i == npass - 2) {
-            if constexpr (v3ok) {
-                float2* srcA = ((i - 1) % 2 == 0) ? work0 : work1;
-                const LoadAny ldA = to_any(LoadC64{srcA, plan.n}, P, batch);
-                if (ldA.kind == kLdTma) {
-                    FusedPair f;
-                    cudaError_t e = fused_prepare(plan, batch, f);
-                    if (e != cudaSuccess) return e;
-                    char name[96];
-                    snprintf(name, sizeof(name), "%s/fused_R%dxR%d", tag, P.R, passes[i + 1].R);
-                    ProfileScope scope(name, plain + (out_bytes > 0 ? out_bytes : plain), stream);
-                    return v3_fused_dispatch(P.fast_id, passes[i + 1].fast_id, SIGN, f, ldA, to_any(st), stream);
-                }
-            }
-        }
         float2* src = ((i - 1) % 2 == 0) ? work0 : work1;
         float2* dst = (i % 2 == 0) ? work0 : work1;
         LoadC64 lmid{src, plan.n};

@@ -468,16 +468,6 @@ struct FftPlan {
     int nfast = 0;                 // register-radix passes (rc_fft3.cuh) when n splits into curated lengths
     FftPass fast[kMaxPasses];
     int max_passes() const { return npass > nfast ? npass : nfast; }
-    // fused last two passes (rc_fused.cuh): L2-resident ring + per-chunk counters
-    struct Fuse {
-        bool ok = false;
-        int W = 32, lag = 6, nslot = 12;
-        float2* ring = nullptr;
-        long long slot_elems = 0;
-        int* counters = nullptr;       // [err | doneA[cap] | doneB[cap]]
-        long long cap = 0;
-    };
-    mutable Fuse fuse;
     struct TableStore* store = nullptr;
 };
 
@@ -700,15 +690,6 @@ inline cudaError_t fft_fill_pass(FftPass& P, long long n, int R, int T, long lon
 #define RC_V3_ALL(X) RC_V3_GROUP0(X) RC_V3_GROUP1(X) RC_V3_GROUP2(X) RC_V3_GROUP3(X)
 constexpr int kV3Groups = 4;
 
-// (pass A id, pass B id) pairs the fused last-two-passes kernel (rc_fused.cuh) is compiled for
-#define RC_FUSED_LIST(X) X(24, 24) X(27, 24) X(27, 27)
-inline bool v3_fused_supported(int id_a, int id_b) {
-#define RC_FUSED_Q(a, b) if (id_a == a && id_b == b) return true;
-    RC_FUSED_LIST(RC_FUSED_Q)
-#undef RC_FUSED_Q
-    return false;
-}
-
 struct V3Entry { int id, R0, R1, R2, threads, cp, role; int R() const { return R0 * R1 * R2; } };
 inline const std::vector<V3Entry>& v3_table() {
     static const std::vector<V3Entry> t = {
@@ -720,10 +701,7 @@ inline const std::vector<V3Entry>& v3_table() {
 }
 // schedule of length R usable as the first (first = true) or as a later pass of a plan
 // 64-column variants (cp = 32: 512-byte rows, one warp per row) are preferred for later passes
-// unless the fused pair kernel, which is compiled for 32-column tiles, was asked for.
-inline bool v3_wide64() {       // read at plan build, not cached: the tests toggle RC_FUSE
-    return getenv("RC_FUSE") == nullptr && getenv("RC_NO_WIDE64") == nullptr;
-}
+inline bool v3_wide64() { return getenv("RC_NO_WIDE64") == nullptr; }
 inline const V3Entry* v3_find(int R, bool first) {
     const V3Entry* hit = nullptr;
     for (const V3Entry& e : v3_table()) {
@@ -876,26 +854,6 @@ inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store)
             Ns *= Fs[i];
         }
         plan.store = &store;
-        const int na = plan.nfast - 2, nb = plan.nfast - 1;
-        // Off by default: on B200 the fused kernel halves the DRAM traffic of the pair (ncu: only the
-        // pair's input and output reach HBM) but its per-tile dependency look-ups and the two roles'
-        // register footprint leave it latency-bound at these small tile sizes (cfg3: 2.3 ms fused vs
-        // 1.44 ms for the two separate passes).  RC_FUSE=1 enables it.
-        if (plan.nfast >= 3 && getenv("RC_FUSE") && n < (1LL << 31) &&
-            v3_fused_supported(plan.fast[na].fast_id, plan.fast[nb].fast_id)) {
-            FftPlan::Fuse& fz = plan.fuse;
-            if (const char* env = getenv("RC_FUSE_W")) fz.W = atoi(env) / 32 * 32;
-            if (fz.W < 32) fz.W = 32;
-            if (const char* env = getenv("RC_FUSE_LAG")) fz.lag = atoi(env);
-            if (const char* env = getenv("RC_FUSE_NSLOT")) fz.nslot = atoi(env);
-            if (fz.lag < 1) fz.lag = 1;
-            if (fz.nslot <= fz.lag) fz.nslot = fz.lag + 2;
-            fz.slot_elems = (long long)plan.fast[na].R * plan.fast[nb].R * fz.W;
-            cudaError_t err = cudaSuccess;
-            fz.ring = (float2*)store.alloc((size_t)fz.nslot * fz.slot_elems * sizeof(float2), &err);
-            if (err != cudaSuccess) return err;
-            fz.ok = fz.ring != nullptr;
-        }
     }
     return cudaSuccess;
 }

@@ -263,8 +263,7 @@ RC_HD void v3_stage1(float4* tile, const float2* tw, int tid) {
 }
 
 // Where the outputs of one column pair of a later pass go: element K of column A at
-// oa + K*ns, of column B at ob + K*ns (default: the Stockham position in the batch entry;
-// the fused pass pairs of rc_fused.cuh point it into their L2-resident ring instead).
+// oa + K*ns, of column B at ob + K*ns (the Stockham position in the batch entry).
 struct V3Out {
     long long oa, ob, ns;
     bool act_a, act_b, pair;

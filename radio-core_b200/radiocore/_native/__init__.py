@@ -52,7 +52,6 @@ _SIGNATURES = {
     "rc_pll_destroy": ([_vp], _int),
     "rc_pll_step": ([_vp, _fp, _vp], _int),
     "rc_pll_eval": ([_vp, _dbl, _int, _fp, _vp], _int),
-    "rc_fused_errors": ([], _int),
     "rc_profile_enable": ([_int], _int),
     "rc_profile_reset": ([], _int),
     "rc_profile_launches": ([], _i64),

@@ -74,6 +74,19 @@ def tuner_offgrid_fm(impl, np_=np):
     return out
 
 
+def tuner_single_channel(impl, np_=np):
+    """One channel and no request_bandwidth: the plan's input bandwidth equals the channel's
+    (tuner.py:163-174), so Tuner.run is window multiply + inverse FFT of every bin (num == Nx)."""
+    B, A = 24000, 4800
+    tuner = impl.Tuner()
+    tuner.add_channel(98.7e6, B, impl.MFM(B, A))
+    x = synth.wideband(B, [0.0], B, seed=12)
+    tuner.load(x)
+    iq = tuner.run(0)
+    return {"f_in": np.array([tuner.input_frequency, tuner.input_bandwidth]), "iq": _f64(iq),
+            "audio": _f64(tuner.channels()[0].demodulator.run(iq))}
+
+
 def fm_direct(impl, np_=np):
     B, A = 25000, 4800
     x = synth.station(B, B, 3, offset_hz=1234.0, deviation=0.3 * B).astype(np.complex64)
@@ -145,6 +158,7 @@ def bandpass_pll_cases(impl, np_=np):
 CASES = {
     "tuner_mfm": tuner_mfm,
     "tuner_offgrid_fm": tuner_offgrid_fm,
+    "tuner_single_channel": tuner_single_channel,
     "fm_direct": fm_direct,
     "wbfm_direct": wbfm_direct,
     "wbfm_50us": wbfm_50us,
