@@ -132,6 +132,22 @@ static std::vector<double> autocorr_taps(const std::vector<float>& b) {
     return g;
 }
 
+// FiltFiltEw for taps g (2K+1 values); the folded fp32 interior path is enabled for the 81-tap
+// pilot filter (K == kFoldK) unless RC_NO_FOLD is set (kernel experiments).
+static FiltFiltEw make_filtfilt(const float* x, float* out, const double* d_g, const std::vector<double>& g_host,
+                                long long n, int K) {
+    FiltFiltEw f{};
+    f.x = x; f.out = out; f.g = d_g; f.n = n; f.K = K;
+    f.fold.on = 0;
+    if (K == kFoldK && (int)g_host.size() == 2 * K + 1 && getenv("RC_NO_FOLD") == nullptr) {
+        f.fold.on = 1;
+        f.fold.gc = g_host[K];
+        f.fold.g[0] = 0.f;
+        for (int d = 1; d <= K; d++) f.fold.g[d] = (float)g_host[K + d];
+    }
+    return f;
+}
+
 static std::vector<float2> unit_circle_table(long long n, long long count, int sign) {
     std::vector<float2> t((size_t)count);
     for (long long k = 0; k < count; k++) {
@@ -290,7 +306,7 @@ struct DemodBank {
             RC_API_CUDA((fft_exec<+1>(planBh, batch, LoadC64{ZpB, h}, StoreC64{(float2*)mpx, h, 1.0f}, w0, w1, st,
                                   "wbfm.irfft_mpx")), "ifft mpx");
             // pilot = Bandpass(19 kHz +- 50, 41 taps).run(mpx)   (wbfm.py:45-46,80)
-            RC_API_CUDA(launch_filtfilt(FiltFiltEw{mpx, pilot, d_g, B, gK}, batch, st, "wbfm.pilot_filtfilt", g_host.data()),
+            RC_API_CUDA(launch_filtfilt(make_filtfilt(mpx, pilot, d_g, g_host, B, gK), batch, st, "wbfm.pilot_filtfilt", g_host.data()),
                         "pilot filtfilt");
             // PLL.step (hilbert) + image(2) * mpx * 1.0175      (wbfm.py:80-83)
             RC_API_CUDA((fft_exec<-1>(planBh, batch, LoadC64{(const float2*)pilot, h}, StoreC64{Z2, h, 1.0f}, w0, w1, st,
@@ -785,7 +801,7 @@ int rc_bandpass_run(rc_bandpass* b, const float* in, float* outp, void* stream) 
     if (b->size <= 3 * (long long)b->taps.size())
         return fail(RC_ERR_INVALID, "The length of the input vector x must be greater than padlen");
     DeviceGuard g(b->device);
-    RC_API_CUDA(launch_filtfilt(FiltFiltEw{in, outp, b->d_g, b->size, b->K}, 1, (cudaStream_t)stream, "filtfilt", b->g_host.data()),
+    RC_API_CUDA(launch_filtfilt(make_filtfilt(in, outp, b->d_g, b->g_host, b->size, b->K), 1, (cudaStream_t)stream, "filtfilt", b->g_host.data()),
                 "filtfilt");
     return RC_OK;
 }

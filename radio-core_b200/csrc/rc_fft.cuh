@@ -746,7 +746,7 @@ inline double fft_pass_cost(int R, bool first) {
 inline bool fft_tuned_split(long long n, std::vector<int>& Rs) {
     struct Row { long long n; int r[4]; };
     static const Row rows[] = {
-        {256000000LL, {640, 800, 500, 0}},
+        {256000000LL, {800, 640, 500, 0}},
         {1000000LL, {200, 50, 100, 0}},
         {500000LL, {200, 50, 50, 0}},
         {250000LL, {500, 500, 0, 0}},

@@ -556,19 +556,58 @@ struct StoreRealPart {
 // exactly  out[n] = sum_j g[j] * xe[n + j - K],  g = b (*) reversed(b),
 // K = len(b)-1, xe = x extended by odd reflection about both end samples.
 // ---------------------------------------------------------------------------
+// Fast interior path for the 81-tap pilot filter of WBFM (K = 40): g is symmetric
+// (g[K-d] = g[K+d]), so
+//   out[n] = g[K] x[n] + sum_{d=1..40} g[K+d] (x[n-d] + x[n+d]).
+// The pair sums and the products run in fp32 (FADD + FFMA, five partial sums of eight distances
+// each), the partial sums are combined in fp64: 10 fp64-pipe operations per sample instead of 81
+// DFMA (the all-fp64 kernel ran at 0.15 of the HBM roofline, bound by the fp64 pipe).  Error of
+// the pilot against the exact sum: ~5e-7 of its amplitude -- the level of the fp32 FFTs around it.
+// Chunks (kFirChunk outputs) that touch the odd-extended block ends keep the exact fp64 path.
+constexpr int kFoldK = 40;
+constexpr int kFoldGroup = 8;
+struct FoldTaps {
+    float g[kFoldK + 1];      // g[d] = (float) gtaps[K + d], d = 1..40 (g[0] unused)
+    double gc;                // centre tap gtaps[K]
+    int on;
+};
+RC_HD float fold_mul_add(float g, float a, float b, float s) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(g, __fadd_rn(a, b), s);
+#else
+    return fmaf(g, a + b, s);
+#endif
+}
+
 struct FiltFiltEw {
     const float* x;
     float* out;
     const double* g;     // 2K+1 autocorrelation taps
     long long n;
     int K;
+    FoldTaps fold;       // fold.on: interior chunks use the folded fp32 path (K == kFoldK only)
     RC_HD double xe(const float* xb, long long i) const {
         if (i < 0) return 2.0 * (double)xb[0] - (double)xb[-i];
         if (i >= n) return 2.0 * (double)xb[n - 1] - (double)xb[2 * (n - 1) - i];
         return (double)xb[i];
     }
+    // does the kFirChunk-output chunk holding sample i stay clear of both block ends?
+    RC_HD bool chunk_interior(long long i) const {
+        const long long c0 = i / 1024 * 1024;
+        return fold.on && c0 >= K && c0 + 1024 + K <= n;
+    }
+    RC_HD float folded(const float* xb, long long i) const {
+        double acc = fold.gc * (double)xb[i];
+        for (int d0 = 1; d0 <= kFoldK; d0 += kFoldGroup) {
+            float sgrp = 0.f;
+            for (int d = d0; d < d0 + kFoldGroup; d++) sgrp = fold_mul_add(fold.g[d], xb[i - d], xb[i + d], sgrp);
+            acc += (double)sgrp;
+        }
+        return (float)acc;
+    }
     RC_HD void operator()(int b, long long i) const {
         const float* xb = x + b * n;
+        if (chunk_interior(i)) { out[b * n + i] = folded(xb, i); return; }
         double acc = 0.0;
         if (i >= K && i + K < n) {
             for (int j = 0; j <= 2 * K; j++) acc += g[j] * (double)xb[i + j - K];
@@ -809,6 +848,94 @@ static __global__ void __launch_bounds__(kFirThreads) filtfilt_kernel(const Filt
         if (n < f.n) f.out[(long long)b * f.n + n] = (float)acc[r];
     }
 }
+
+// Folded pilot filter (FiltFiltEw::folded) for interior chunks: fp32 window in shared memory
+// (one 4-float pad per 32 so that the 16-byte reads of 8 threads, 32 bytes apart, cover all banks),
+// two register windows per thread sliding outwards from the centre, 8 outputs per thread.
+RC_HD int fold_slot(int i) { return i + 4 * (i >> 5); }
+constexpr int kFoldWin = kFirChunk + 2 * kFoldK + 16;
+static __global__ void __launch_bounds__(kFirThreads) filtfilt_fold_kernel(const FiltFiltEw f, const __grid_constant__ FirTapsParam ctaps) {
+    __shared__ __align__(16) float xf[kFoldWin + 4 * (kFoldWin / 32) + 8];
+    __shared__ double xs[kFirSlots];
+    __shared__ double tp[kFirMaxTaps];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const long long n0 = (long long)blockIdx.x * kFirChunk;
+    const float* xb = f.x + (long long)b * f.n;
+    if (!(n0 >= f.K && n0 + kFirChunk + f.K <= f.n)) {
+        // a block end is in reach: exact fp64 path with the odd extension (as filtfilt_kernel)
+        const int ntaps = 2 * f.K + 1, ntaps8 = (ntaps + 7) / 8 * 8;
+        for (int i = tid; i < kFirChunk + ntaps8 + 8; i += kFirThreads) {
+            const long long idx = n0 - f.K + i;
+            xs[fir_slot(i)] = (idx < f.n + f.K) ? f.xe(xb, idx) : 0.0;
+        }
+        for (int i = tid; i < ntaps8; i += kFirThreads) tp[i] = i < ntaps ? f.g[i] : 0.0;
+        __syncthreads();
+        double acc[kFirPer];
+#pragma unroll
+        for (int r = 0; r < kFirPer; r++) acc[r] = 0.0;
+        const int o = tid * kFirPer;
+        if (ctaps.n8 == 88 && ntaps8 == 88) fir_window8_c<88>(xs, ctaps, o, acc);
+        else fir_window8(xs, tp, ntaps8, o, acc);
+#pragma unroll
+        for (int r = 0; r < kFirPer; r++) {
+            const long long n = n0 + o + r;
+            if (n < f.n) f.out[(long long)b * f.n + n] = (float)acc[r];
+        }
+        return;
+    }
+    // window[i] = x[n0 - 40 + i], i in [0, 1024 + 80): 16-byte loads where the source allows
+    const float* src = xb + (n0 - kFoldK);
+    if ((((size_t)src) & 15) == 0) {
+        for (int i = tid; i < (kFirChunk + 2 * kFoldK) / 4; i += kFirThreads)
+            *(float4*)(xf + fold_slot(4 * i)) = __ldg((const float4*)src + i);
+    } else {
+        for (int i = tid; i < kFirChunk + 2 * kFoldK; i += kFirThreads) xf[fold_slot(i)] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int c = tid * kFirPer + kFoldK;          // window index of this thread's first output (multiple of 8)
+    float lw[16], rw[16];
+    {
+        const float4 a = *(const float4*)(xf + fold_slot(c)), d = *(const float4*)(xf + fold_slot(c + 4));
+        lw[8] = rw[0] = a.x; lw[9] = rw[1] = a.y; lw[10] = rw[2] = a.z; lw[11] = rw[3] = a.w;
+        lw[12] = rw[4] = d.x; lw[13] = rw[5] = d.y; lw[14] = rw[6] = d.z; lw[15] = rw[7] = d.w;
+    }
+    double acc[kFirPer];
+#pragma unroll
+    for (int r = 0; r < kFirPer; r++) acc[r] = f.fold.gc * (double)rw[r];
+#pragma unroll
+    for (int m = 0; m < kFoldK / kFoldGroup; m++) {
+        // left window: x[c - 8(m+1) .. +15], its upper half is the previous group's lower half;
+        // right window: x[c + 8m .. +15], its lower half is the previous group's upper half
+#pragma unroll
+        for (int i = 0; i < 8; i++) { lw[8 + i] = m == 0 ? lw[8 + i] : lw[i]; rw[i] = m == 0 ? rw[i] : rw[8 + i]; }
+        {
+            const int lb = c - 8 * (m + 1), rb = c + 8 * m + 8;
+            const float4 a = *(const float4*)(xf + fold_slot(lb)), d = *(const float4*)(xf + fold_slot(lb + 4));
+            lw[0] = a.x; lw[1] = a.y; lw[2] = a.z; lw[3] = a.w; lw[4] = d.x; lw[5] = d.y; lw[6] = d.z; lw[7] = d.w;
+            const float4 e = *(const float4*)(xf + fold_slot(rb)), h = *(const float4*)(xf + fold_slot(rb + 4));
+            rw[8] = e.x; rw[9] = e.y; rw[10] = e.z; rw[11] = e.w; rw[12] = h.x; rw[13] = h.y; rw[14] = h.z; rw[15] = h.w;
+        }
+        float sg[kFirPer];
+#pragma unroll
+        for (int r = 0; r < kFirPer; r++) sg[r] = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < kFoldGroup; jj++) {
+            const float g = f.fold.g[8 * m + 1 + jj];
+#pragma unroll
+            for (int r = 0; r < kFirPer; r++) sg[r] = fold_mul_add(g, lw[7 - jj + r], rw[1 + jj + r], sg[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kFirPer; r++) acc[r] += (double)sg[r];
+    }
+    float* o = f.out + (long long)b * f.n + n0 + tid * kFirPer;
+    if ((((size_t)o) & 15) == 0) {
+        *(float4*)o = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
+        *(float4*)(o + 4) = make_float4((float)acc[4], (float)acc[5], (float)acc[6], (float)acc[7]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < kFirPer; r++) o[r] = (float)acc[r];
+    }
+}
 #endif
 
 inline int epi_chunks(long long A) { return (int)((A + kFirChunk - 1) / kFirChunk); }
@@ -874,7 +1001,9 @@ inline cudaError_t launch_filtfilt(const FiltFiltEw& f, int batch, cudaStream_t 
         for (int i = 0; i < ntaps; i++) ct.t[i] = g_host[i];
         ct.n8 = 88;
     }
-    filtfilt_kernel<<<dim3((unsigned)((f.n + kFirChunk - 1) / kFirChunk), (unsigned)batch), kFirThreads, 0, stream>>>(f, ct);
+    const dim3 grid((unsigned)((f.n + kFirChunk - 1) / kFirChunk), (unsigned)batch);
+    if (f.fold.on && f.K == kFoldK) filtfilt_fold_kernel<<<grid, kFirThreads, 0, stream>>>(f, ct);
+    else filtfilt_kernel<<<grid, kFirThreads, 0, stream>>>(f, ct);
     return cudaGetLastError();
 #endif
 }
