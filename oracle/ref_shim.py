@@ -1,9 +1,10 @@
-"""Import the real reference (read-only, /root/reference) in the BUILD container.
+"""Import the real, unmodified reference package under the name ``_ref_radiocore``.
 
-TEST INFRASTRUCTURE ONLY.  ``/root/reference`` does not exist on the GPU box,
-so nothing here is used by ``-m gpu`` tests, ``smoke()`` or ``bench.py``; it
-exists to (a) validate ``radiocore_oracle.py`` live and (b) generate the golden
-vectors under ``tests/golden/`` (``tests/golden/make_golden.py``).
+TEST / BASELINE INFRASTRUCTURE ONLY.  Source, in order: ``$RADIOCORE_REFERENCE``,
+``/root/reference`` (build container, read-only), ``oracle/_ref`` (the byte-for-byte copy that
+``oracle/make_ref.py`` makes so that the reference travels to the GPU box).  Used to (a) validate
+``radiocore_oracle.py`` live, (b) generate the golden vectors under ``tests/golden/``
+(``tests/golden/make_golden.py``) and (c) time the reference itself in ``bench.py``'s CPU legs.
 
 The reference's package ``__init__`` imports ``atomics`` (PyPI, absent here)
 through ``radiocore/tools/ringbuffer.py:3``; only RingBuffer uses it, so an
@@ -14,7 +15,15 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RADIOCORE_REFERENCE", "/root/reference")
+def _find_root():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get("RADIOCORE_REFERENCE"), "/root/reference", os.path.join(here, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "radiocore")):
+            return cand
+    return os.environ.get("RADIOCORE_REFERENCE", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
