@@ -69,6 +69,26 @@ int rc_engine_spectrum(rc_engine* e, void* spectrum_out_dev, void* stream);
 int rc_engine_reset_state(rc_engine* e);
 int rc_engine_workspace_bytes(rc_engine* e, int64_t* bytes);
 
+/* ---- Tuner.load sharded over the GPUs of one box (radiocore/tools/sharding.py) -------------
+ * The reference computes the whole N-point spectrum in one place (tuner.py:137-138).  With G
+ * ranks, rank g transforms its commutator branch x[G m + g] (rc_fft_exec, M = N/G points), the
+ * ranks exchange pieces over NVLink, rc_subband_combine does the remaining radix-G step, and a
+ * second exchange leaves on every rank the contiguous sub-band [x_lo, x_lo + x_len) (cyclic bin
+ * indices of the N-bin spectrum) its own channels read.  rc_engine_set_subband (before commit)
+ * tells the engine that it will be handed such a sub-band instead of a block;
+ * rc_engine_load_subband = Tuner.load for it: no copy, the engine reads `spectrum_dev` during
+ * the following rc_engine_run / rc_engine_channel_iq.  rc_engine_load is refused in this mode. */
+int rc_engine_set_subband(rc_engine* e, int64_t x_lo, int64_t x_len);
+int rc_engine_load_subband(rc_engine* e, const void* spectrum_dev);
+int rc_subband_combine(int device, int n_ranks, int64_t piece_len, int64_t n_input, int64_t k0_base,
+                       const void* pieces_dev /* [G][P] complex64 */, void* bins_dev /* [G][P] */, void* stream);
+
+/* ---- persistent complex FFT plan (batched, in != out): the local transform of the sharded load */
+typedef struct rc_fft rc_fft;
+int rc_fft_create(int device, int64_t n, int batch, rc_fft** out);
+int rc_fft_destroy(rc_fft* f);
+int rc_fft_exec(rc_fft* f, int sign, const void* in_dev, void* out_dev, void* stream);
+
 /* ---- standalone demodulators: FM.run / MFM.run / WBFM.run on `batch` blocks */
 typedef struct rc_demod rc_demod;
 int rc_demod_create(int device, int mode, int64_t input_size, int64_t output_size,

@@ -364,6 +364,15 @@ struct rc_engine {
     long long* d_roll_all = nullptr;
     float2* y_single = nullptr; size_t y_single_len = 0;
     long long audio_total = 0;
+    // sub-band mode (rc_engine_set_subband): X is handed in per block and holds bins
+    // [x_lo, x_lo + x_len) of the N-bin spectrum; rolls are shifted by x_lo
+    bool subband = false;
+    long long x_lo = 0, x_len = 0;
+    long long shifted_roll(long long roll) const {
+        long long r = ((roll % N) + N) % N;
+        if (subband) r = (r + x_lo) % N;
+        return r;
+    }
 };
 
 extern "C" {
@@ -410,10 +419,19 @@ int rc_engine_commit(rc_engine* e) {
     if (e->committed) return fail(RC_ERR_STATE, "engine: already committed");
     if (e->chans.empty()) return fail(RC_ERR_STATE, "engine: no channels");
     DeviceGuard g(e->device);
-    RC_API_CUDA(fft_plan_build(e->planN, e->N, e->store), "plan N");
-    RC_API_CUDA(e->arena.alloc(&e->X, (size_t)e->N), "alloc X");
-    if (e->planN.max_passes() >= 2) RC_API_CUDA(e->arena.alloc(&e->wN0, (size_t)e->N), "alloc wN0");
-    if (e->planN.max_passes() >= 3) RC_API_CUDA(e->arena.alloc(&e->wN1, (size_t)e->N), "alloc wN1");
+    if (e->subband) {
+        // every bin a channel gathers -- (i - roll - x_lo) mod N for i in [-B/2, B/2] -- must lie
+        // inside the sub-band the engine will be handed
+        for (auto& c : e->chans) {
+            const long long first = (((-(c.B / 2) - c.roll - e->x_lo) % e->N) + e->N) % e->N;
+            if (first + c.B + 1 > e->x_len) return fail(RC_ERR_INVALID, "engine: a channel reads bins outside the sub-band");
+        }
+    } else {
+        RC_API_CUDA(fft_plan_build(e->planN, e->N, e->store), "plan N");
+        RC_API_CUDA(e->arena.alloc(&e->X, (size_t)e->N), "alloc X");
+        if (e->planN.max_passes() >= 2) RC_API_CUDA(e->arena.alloc(&e->wN0, (size_t)e->N), "alloc wN0");
+        if (e->planN.max_passes() >= 3) RC_API_CUDA(e->arena.alloc(&e->wN1, (size_t)e->N), "alloc wN1");
+    }
     // group channels with identical demodulator configuration
     size_t maxB = 0;
     for (size_t i = 0; i < e->chans.size(); i++) {
@@ -447,7 +465,7 @@ int rc_engine_commit(rc_engine* e) {
         if (rc) return rc;
         bk.planB = &e->planB[c0.B];
         std::vector<long long> rolls;
-        for (int m : bk.members) rolls.push_back(((e->chans[m].roll % e->N) + e->N) % e->N);
+        for (int m : bk.members) rolls.push_back(e->shifted_roll(e->chans[m].roll));
         RC_API_CUDA(e->arena.upload(&bk.d_roll, rolls), "rolls");
         RC_API_CUDA(e->arena.alloc(&bk.ang, (size_t)batch * c0.B), "alloc angle");
         if (bk.planB->max_passes() >= 2) RC_API_CUDA(e->arena.alloc(&bk.w0, (size_t)batch * c0.B), "alloc yw0");
@@ -457,7 +475,7 @@ int rc_engine_commit(rc_engine* e) {
     }
     e->audio_total = off;
     std::vector<long long> all;
-    for (auto& c : e->chans) all.push_back(((c.roll % e->N) + e->N) % e->N);
+    for (auto& c : e->chans) all.push_back(e->shifted_roll(c.roll));
     RC_API_CUDA(e->arena.upload(&e->d_roll_all, all), "rolls all");
     e->y_single_len = maxB;
     RC_API_CUDA(e->arena.alloc(&e->y_single, maxB * 2), "alloc y_single");
@@ -498,11 +516,31 @@ int rc_engine_workspace_bytes(rc_engine* e, int64_t* bytes) {
 // Tuner.load (tuner.py:137-138): X = fft(iq), complex64 in / complex64 out.
 int rc_engine_load(rc_engine* e, const void* iq_dev, void* stream) {
     if (!e || !e->committed) return fail(RC_ERR_STATE, "engine: load before commit");
+    if (e->subband) return fail(RC_ERR_STATE, "engine: sub-band mode takes rc_engine_load_subband");
     if (!iq_dev) return fail(RC_ERR_INVALID, "engine: null input");
     DeviceGuard g(e->device);
     cudaStream_t st = (cudaStream_t)stream;
     RC_API_CUDA((fft_exec<-1>(e->planN, 1, LoadC64{(const float2*)iq_dev, e->N}, StoreC64{e->X, e->N, 1.0f},
                               e->wN0, e->wN1, st, "tuner.load_fft")), "tuner load fft");
+    e->loaded = true;
+    return RC_OK;
+}
+
+int rc_engine_set_subband(rc_engine* e, int64_t x_lo, int64_t x_len) {
+    if (!e) return fail(RC_ERR_INVALID, "engine: null handle");
+    if (e->committed) return fail(RC_ERR_STATE, "engine: set_subband after commit");
+    if (x_len < 2 || x_len > e->N || x_lo < 0 || x_lo >= e->N) return fail(RC_ERR_INVALID, "engine: sub-band outside the spectrum");
+    e->subband = true;
+    e->x_lo = x_lo;
+    e->x_len = x_len;
+    return RC_OK;
+}
+
+// Tuner.load for a sub-band produced elsewhere (sharded load): adopt the pointer, no copy.
+int rc_engine_load_subband(rc_engine* e, const void* spectrum_dev) {
+    if (!e || !e->committed || !e->subband) return fail(RC_ERR_STATE, "engine: load_subband needs a committed sub-band engine");
+    if (!spectrum_dev) return fail(RC_ERR_INVALID, "engine: null spectrum");
+    e->X = (float2*)spectrum_dev;
     e->loaded = true;
     return RC_OK;
 }
@@ -549,8 +587,8 @@ int rc_engine_channel_iq(rc_engine* e, int index, void* out, void* stream) {
 int rc_engine_spectrum(rc_engine* e, void* out, void* stream) {
     if (!e || !e->committed || !e->loaded) return fail(RC_ERR_STATE, "engine: spectrum before load");
     DeviceGuard g(e->device);
-    RC_API_CUDA(dev_copy(out, e->X, (size_t)e->N * sizeof(float2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream),
-                "spectrum copy");
+    RC_API_CUDA(dev_copy(out, e->X, (size_t)(e->subband ? e->x_len : e->N) * sizeof(float2), cudaMemcpyDeviceToDevice,
+                         (cudaStream_t)stream), "spectrum copy");
     return RC_OK;
 }
 
@@ -904,6 +942,67 @@ int rc_profile_report(char* buf, int capacity) {
         buf[capacity - 1] = 0;
     }
     return (int)out.size() + 1;
+}
+
+// ------------------------------------------------------- sharded-load pieces
+int rc_subband_combine(int device, int n_ranks, int64_t piece_len, int64_t n_input, int64_t k0_base,
+                       const void* pieces_dev, void* bins_dev, void* stream) {
+    if (!pieces_dev || !bins_dev || piece_len < 1 || n_input < 1 || k0_base < 0)
+        return fail(RC_ERR_INVALID, "subband_combine: bad argument");
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double bytes = 16.0 * (double)piece_len * n_ranks;
+    const float2* F = (const float2*)pieces_dev;
+    float2* Y = (float2*)bins_dev;
+    const double m2n = -2.0 / (double)n_input;
+    cudaError_t err;
+    switch (n_ranks) {
+        case 2: err = launch_ew(piece_len, 1, SubbandCombineEw<2>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 4: err = launch_ew(piece_len, 1, SubbandCombineEw<4>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 8: err = launch_ew(piece_len, 1, SubbandCombineEw<8>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 16: err = launch_ew(piece_len, 1, SubbandCombineEw<16>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        default: return fail(RC_ERR_UNSUPPORTED, "subband_combine: 2, 4, 8 or 16 ranks");
+    }
+    RC_API_CUDA(err, "subband combine");
+    return RC_OK;
+}
+
+struct rc_fft {
+    int device = 0, batch = 1;
+    long long n = 0;
+    TableStore store{kOnDevice};
+    Arena arena;
+    FftPlan plan;
+    float2 *w0 = nullptr, *w1 = nullptr;
+};
+int rc_fft_create(int device, int64_t n, int batch, rc_fft** out) {
+    if (!out || n < 1 || batch < 1) return fail(RC_ERR_INVALID, "fft: bad argument");
+    if (!fft_size_supported(n)) return fail(RC_ERR_UNSUPPORTED, "fft: size must factor into 2^a 3^b 5^c");
+    DeviceGuard g(device);
+    std::unique_ptr<rc_fft> f(new rc_fft());
+    f->device = device; f->n = n; f->batch = batch;
+    RC_API_CUDA(fft_plan_build(f->plan, n, f->store), "plan");
+    if (f->plan.max_passes() >= 2) RC_API_CUDA(f->arena.alloc(&f->w0, (size_t)n * batch), "alloc");
+    if (f->plan.max_passes() >= 3) RC_API_CUDA(f->arena.alloc(&f->w1, (size_t)n * batch), "alloc");
+    RC_API_CUDA(dev_sync(0), "table sync");
+    *out = f.release();
+    return RC_OK;
+}
+int rc_fft_destroy(rc_fft* f) {
+    if (!f) return RC_OK;
+    DeviceGuard g(f->device);
+    delete f;
+    return RC_OK;
+}
+int rc_fft_exec(rc_fft* f, int sign, const void* in, void* outp, void* stream) {
+    if (!f || !in || !outp || in == outp || (sign != 1 && sign != -1)) return fail(RC_ERR_INVALID, "fft: bad argument");
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (sign < 0) e = fft_exec<-1>(f->plan, f->batch, LoadC64{(const float2*)in, f->n}, StoreC64{(float2*)outp, f->n, 1.0f}, f->w0, f->w1, st, "tuner.local_fft");
+    else e = fft_exec<+1>(f->plan, f->batch, LoadC64{(const float2*)in, f->n}, StoreC64{(float2*)outp, f->n, 1.0f}, f->w0, f->w1, st, "tuner.local_fft");
+    RC_API_CUDA(e, "fft exec");
+    return RC_OK;
 }
 
 // ----------------------------------------------------------------- FFT hook

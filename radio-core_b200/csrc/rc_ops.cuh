@@ -550,6 +550,45 @@ struct StoreRealPart {
 };
 
 // ---------------------------------------------------------------------------
+// Sub-band combine: the last, radix-G step of an N-point forward FFT whose first steps were G
+// independent M-point FFTs (M = N / G) of the commutated input x_g[m] = x[G m + g], one per GPU
+// (Tuner.load, tuner.py:137-138, sharded over G ranks -- SURVEY.md 7.3-1 / 8e):
+//   X[k0 + M k1] = sum_g W_G^{g k1} * W_N^{g k0} * F_g[k0],     k0 in [0, M), k1 in [0, G).
+// A rank holds F_g[k0] of ALL g for its piece k0 in [k0_base, k0_base + P) (after the first
+// exchange) and produces the G bins k0 + M k1 of every k0 of the piece: Y[k1][j], j = k0 - k0_base.
+// Twiddle W_N^{k0} from an fp64 sincospi, its powers by fp64 recurrence, rounded to fp32 once --
+// the same accuracy as the inter-pass twiddles of the FFT engine.
+// ---------------------------------------------------------------------------
+template <int G>
+struct SubbandCombineEw {
+    const float2* F;      // [G][P]
+    float2* Y;            // [G][P]
+    long long P, k0_base;
+    double minus_two_over_n;
+    RC_HD void operator()(int, long long j) const {
+        float2 v[G];
+        double sn, cs;
+        const double th = (double)(k0_base + j) * minus_two_over_n;
+#ifdef __CUDA_ARCH__
+        sincospi(th, &sn, &cs);
+#else
+        sn = sin(kPi * th); cs = cos(kPi * th);
+#endif
+        const double2 w1 = make_double2(cs, sn);
+        double2 w = w1;
+        v[0] = ldg(F + j);
+#pragma unroll
+        for (int g = 1; g < G; g++) {
+            v[g] = cmul(ldg(F + (long long)g * P + j), make_float2((float)w.x, (float)w.y));
+            if (g + 1 < G) w = cmul64(w, w1);
+        }
+        Dft<G, -1>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < G; k1++) Y[(long long)k1 * P + j] = v[k1];
+    }
+};
+
+// ---------------------------------------------------------------------------
 // Zero-phase FIR (bandpass.py:72 filtfilt(b, 1, x), padtype 'odd').
 // With an FIR the lfilter_zi start-up terms only touch the first len(b)-1
 // samples of the 3*len(b) extension, which filtfilt crops, so the result is

@@ -31,6 +31,12 @@ _SIGNATURES = {
     "rc_engine_spectrum": ([_vp, _vp, _vp], _int),
     "rc_engine_reset_state": ([_vp], _int),
     "rc_engine_workspace_bytes": ([_vp, C.POINTER(_i64)], _int),
+    "rc_engine_set_subband": ([_vp, _i64, _i64], _int),
+    "rc_engine_load_subband": ([_vp, _vp], _int),
+    "rc_subband_combine": ([_int, _int, _i64, _i64, _i64, _vp, _vp, _vp], _int),
+    "rc_fft_create": ([_int, _i64, _int, _pp], _int),
+    "rc_fft_destroy": ([_vp], _int),
+    "rc_fft_exec": ([_vp, _int, _vp, _vp, _vp], _int),
     "rc_demod_create": ([_int, _int, _i64, _i64, _dbl, _int, _pp], _int),
     "rc_demod_destroy": ([_vp], _int),
     "rc_demod_run": ([_vp, _vp, _fp, _vp], _int),

@@ -115,3 +115,245 @@ class BlockBroadcaster:
 
     def in_flight(self) -> int:
         return len(self._pending)
+
+
+# =====================================================================================
+# Sharded Tuner.load: the N-point FFT itself divided over the ranks
+# =====================================================================================
+# BlockBroadcaster replicates the block, so every GPU repeats the whole N-point FFT
+# (tools/tuner.py:137-138) and receives 8*N bytes per block over NVLink.  The sharded load
+# divides both: with G ranks, M = N/G and P = M/G,
+#
+#   rank g holds the commutator branch x_g[m] = x[G*m + g]                (polyphase input commutator)
+#   F_g = FFT_M(x_g)                                                      local, 1/G of the FFT work
+#   exchange 1 (all-to-all, equal pieces): rank p collects F_g[k0], k0 in [p*P, (p+1)*P), of every g
+#   X[k0 + M*k1] = sum_g W_G^{g k1} W_N^{g k0} F_g[k0]                    the remaining radix-G step, local
+#   exchange 2: rank p sends each rank d the bins of d's sub-band that p now holds
+#
+# after which rank d owns the contiguous (cyclic) sub-band [x_lo_d, x_lo_d + x_len_d) its channels
+# gather from (Tuner.needed_bins) -- a halo of neighbouring bins included, so no channel needs a
+# second rank.  Per rank and block 2 * 8*N/G * (G-1)/G bytes cross NVLink instead of 8*N*(G-1)/G,
+# there is no reduction, and the result is the same N-point DFT (SURVEY.md 7.3-1 with D = G).
+
+
+def covering_arc(intervals: Sequence, n: int):
+    """Smallest cyclic arc (start, length) of Z_n containing every (first, count) interval;
+    start is even (the channel gather stages even-aligned bins by TMA)."""
+    if not intervals:
+        raise ValueError("no intervals")
+    best = None
+    starts = sorted({int(s) % n for s, _ in intervals})
+    for s0 in starts:
+        length = max(((int(s) - s0) % n) + int(c) for s, c in intervals)
+        if best is None or length < best[1]:
+            best = (s0, length)
+    lo, length = best
+    if lo % 2:
+        lo, length = lo - 1, length + 1
+    return lo % n, min(length, n)
+
+
+def _arc_parts(lo: int, length: int, n: int):
+    """The cyclic arc as linear (first_bin, count, position_in_arc) parts of [0, n)."""
+    if lo + length <= n:
+        return [(lo, length, 0)]
+    return [(lo, n - lo, 0), (0, lo + length - n, n - lo)]
+
+
+class SubbandPlan:
+    """Who sends which bins to whom in exchange 2 (pure host arithmetic; every rank builds the
+    same plan from the list of all ranks' arcs)."""
+
+    def __init__(self, n: int, world: int, arcs: Sequence):
+        if n % (world * world):
+            raise ValueError("the block length must be a multiple of world_size**2")
+        self.n, self.world = int(n), int(world)
+        self.m = self.n // self.world            # local FFT length, and the stride between a piece's bin blocks
+        self.p = self.m // self.world            # piece length
+        self.arcs = [(int(a), int(b)) for a, b in arcs]
+
+    def runs(self, src: int, dst: int):
+        """[(k1, j_lo, j_hi, pos)]: rank ``src`` holds bins k1*M + src*P + j as Y[k1][j]; those with
+        j in [j_lo, j_hi) go to position ``pos`` onward of ``dst``'s sub-band.  Ordered by (k1, part)
+        -- the order both ends enumerate them in."""
+        out = []
+        lo, length = self.arcs[dst]
+        for k1 in range(self.world):
+            a = k1 * self.m + src * self.p               # first bin of this block of the piece
+            for first, count, pos0 in _arc_parts(lo, length, self.n):
+                b0, b1 = max(a, first), min(a + self.p, first + count)
+                if b0 < b1:
+                    out.append((k1, b0 - a, b1 - a, pos0 + (b0 - first)))
+        return out
+
+
+class ShardedLoad:
+    """Distributed ``Tuner.load``: every rank posts its commutator branch of the block and takes
+    back the sub-band of the spectrum its own channels need.
+
+        load = ShardedLoad(tuner)          # after the channels are registered (collective: arcs are exchanged)
+        load.post(x_branch)                # x[rank::world] of block k+1: local FFT, exchanges, combine -- on a side stream
+        tuner.load_subband(load.take())    # block k: ordered after its arrival
+        audio = tuner.run_all()
+
+    ``depth`` sub-band buffers rotate, so block k+1 travels while block k is in the channel kernels.
+    ``kernels`` supplies the local arithmetic (the CUDA library by default; the gloo CPU tests pass
+    a NumPy stand-in to check the plan and the exchanges).
+    """
+
+    def __init__(self, tuner, depth: int = 2, kernels=None, group=None):
+        self._world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._group = group
+        n = int(tuner.input_bandwidth)
+        arc = covering_arc(tuner.needed_bins(), n)
+        arcs = [None] * self._world
+        if self._world > 1:
+            dist.all_gather_object(arcs, arc, group=group)
+        else:
+            arcs = [arc]
+        self.plan = SubbandPlan(n, self._world, arcs)
+        self.x_lo, self.x_len = arcs[self._rank]
+        tuner.set_subband(self.x_lo, self.x_len)
+        self._k = kernels if kernels is not None else _NativeKernels(self.plan, self._rank)
+        k, plan = self._k, self.plan
+        self._F = k.empty(plan.m)                                   # F_g, natural order: piece p = [p*P, (p+1)*P)
+        self._R = k.empty(plan.m)                                   # [G][P]: piece `rank` of every F_g
+        self._Y = k.empty(plan.m)                                   # [G][P]: bins k1*M + rank*P + j
+        pad = 1 << 16                                               # the gather's tensor map describes whole rows past x_len
+        self._slots = [k.empty(self.x_len + pad) for _ in range(max(2, depth))]
+        self._depth = max(2, depth)
+        self._turn = 0
+        self._pending = collections.deque()
+        self._send = [plan.runs(self._rank, d) for d in range(self._world)]
+        self._recv = [plan.runs(p, self._rank) for p in range(self._world)]
+        self.bytes_exchanged = 8 * (2 * plan.m - 2 * plan.p) if self._world > 1 else 0   # sent per block, both exchanges (halo aside)
+
+    # ---- the two exchanges
+    def _exchange_pieces(self):
+        """R[g] = F_g[rank*P : (rank+1)*P] from every rank g (equal-split all-to-all)."""
+        if self._world == 1:
+            self._R.copy_(self._F)
+            return
+        out, inp = _as_real(self._R), _as_real(self._F)
+        if dist.get_backend(self._group) == "nccl":
+            dist.all_to_all_single(out, inp, group=self._group)
+            return
+        p, ops = self.plan.p, []
+        for r in range(self._world):
+            if r == self._rank:
+                out[r * p:(r + 1) * p].copy_(inp[r * p:(r + 1) * p])
+            else:
+                ops.append(dist.P2POp(dist.isend, inp[r * p:(r + 1) * p], r, group=self._group))
+                ops.append(dist.P2POp(dist.irecv, out[r * p:(r + 1) * p], r, group=self._group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def _exchange_bins(self, slot):
+        """Exchange 2: the runs of SubbandPlan straight from Y into the destination sub-bands."""
+        p = self.plan.p
+        Y, X = _as_real(self._Y), _as_real(slot)
+        ops = []
+        for d in range(self._world):
+            for k1, j0, j1, pos in self._send[d]:
+                src = Y[k1 * p + j0: k1 * p + j1]
+                if d == self._rank:
+                    X[pos: pos + (j1 - j0)].copy_(src)
+                else:
+                    ops.append(dist.P2POp(dist.isend, src, d, group=self._group))
+        for q in range(self._world):
+            if q == self._rank:
+                continue
+            for k1, j0, j1, pos in self._recv[q]:
+                ops.append(dist.P2POp(dist.irecv, X[pos: pos + (j1 - j0)], q, group=self._group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    # ---- block interface
+    def post(self, x_branch) -> None:
+        """Start the load of the next block from this rank's branch x[rank::world] (M samples)."""
+        if len(self._pending) >= self._depth:
+            raise RuntimeError("too many blocks in flight: take() before the next post()")
+        if x_branch.numel() != self.plan.m:
+            raise ValueError("the branch holds N / world_size samples")
+        slot = self._slots[self._turn]
+        self._turn = (self._turn + 1) % self._depth
+        done = self._k.begin(x_branch, slot)
+        self._k.fft(x_branch, self._F)
+        self._exchange_pieces()
+        self._k.combine(self._R, self._Y, self._rank * self.plan.p)
+        self._exchange_bins(slot)
+        self._pending.append((slot, self._k.end(done)))
+
+    def take(self):
+        """Sub-band of the oldest posted block (bins [x_lo, x_lo + x_len)), ordered after its arrival."""
+        if not self._pending:
+            raise RuntimeError("take() without a posted block")
+        slot, ev = self._pending.popleft()
+        self._k.wait(ev, slot)
+        return slot
+
+    def in_flight(self) -> int:
+        return len(self._pending)
+
+
+def _as_real(t):
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+class _NativeKernels:
+    """Local arithmetic of ShardedLoad on the GPU (C ABI: rc_fft_*, rc_subband_combine); the whole
+    pipeline of a block runs on a side stream so that it overlaps the channel kernels of the
+    previous block on the caller's stream."""
+
+    def __init__(self, plan, rank):
+        import ctypes as C
+        from radiocore import _device, _native
+        self._native, self._C = _native, C
+        self._plan = plan
+        self._dev = _device.device_index()
+        self._stream = torch.cuda.Stream()
+        self._fft = C.c_void_p()
+        _native.check(_native.lib().rc_fft_create(self._dev, plan.m, 1, C.byref(self._fft)))
+        self._ctx = None
+        self._readers = {}            # sub-band buffer -> event of the last channel kernels that read it
+
+    def __del__(self):
+        h, self._fft = getattr(self, "_fft", None), None
+        if h:
+            try:
+                self._native.lib().rc_fft_destroy(h)
+            except Exception:
+                pass
+
+    def empty(self, n):
+        return torch.empty(int(n), dtype=torch.complex64, device="cuda")
+
+    def begin(self, x_branch, slot):
+        cur = torch.cuda.current_stream()
+        self._stream.wait_stream(cur)                     # the producer of x_branch, and the previous readers of `slot`
+        x_branch.record_stream(self._stream)
+        self._ctx = torch.cuda.stream(self._stream)
+        self._ctx.__enter__()
+        return None
+
+    def fft(self, x, out):
+        x = x.contiguous()
+        self._native.check(self._native.lib().rc_fft_exec(self._fft, -1, x.data_ptr(), out.data_ptr(),
+                                                          self._stream.cuda_stream))
+
+    def combine(self, pieces, bins, k0_base):
+        p = self._plan
+        self._native.check(self._native.lib().rc_subband_combine(
+            self._dev, p.world, p.p, p.n, int(k0_base), pieces.data_ptr(), bins.data_ptr(), self._stream.cuda_stream))
+
+    def end(self, _):
+        ev = torch.cuda.Event()
+        ev.record(self._stream)
+        self._ctx.__exit__(None, None, None)
+        self._ctx = None
+        return ev
+
+    def wait(self, ev, slot):
+        torch.cuda.current_stream().wait_event(ev)

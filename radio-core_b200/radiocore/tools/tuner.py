@@ -55,6 +55,7 @@ class Tuner:
         self._audio_serial = -1
         self._host_serial = -1
         self._input_ref = None
+        self._subband = None       # (x_lo, x_len): the engine is handed a sub-band of the spectrum (sharding.ShardedLoad)
         self._stage_dev = None     # persistent device copy of a pinned host block (load)
         self._stage_ev = None
         self._pipe = None          # block pipeline state of submit()/collect()
@@ -133,7 +134,7 @@ class Tuner:
                 spec.append((roll, int(ch.bandwidth), d._output_size, d._mode, d._deemphasis_rate))
             else:
                 spec.append((roll, int(ch.bandwidth), 2, MODE_NONE, 75e-6))
-        return n, tuple(spec)
+        return n, tuple(spec), self._subband
 
     def _ensure_engine(self):
         if not self._bounds:
@@ -143,12 +144,14 @@ class Tuner:
             return
         self._drop_engine()
         lib = _native.lib()
-        n, spec = key
+        n, spec, subband = key
         h = C.c_void_p()
         _native.check(lib.rc_engine_create(_device.device_index(), n, C.byref(h)))
         try:
             for roll, bw, audio, mode, tau in spec:
                 _native.check(lib.rc_engine_add_channel(h, roll, bw, audio, mode, tau, None))
+            if subband is not None:
+                _native.check(lib.rc_engine_set_subband(h, int(subband[0]), int(subband[1])))
             _native.check(lib.rc_engine_commit(h))
         except Exception:
             lib.rc_engine_destroy(h)
@@ -175,6 +178,36 @@ class Tuner:
         x = self._stage_input(input_signal)
         self._input_ref = x
         _native.check(_native.lib().rc_engine_load(self._engine, x.data_ptr(), _device.stream_ptr()))
+        self._serial += 1
+
+    # ------------------------------------------------ sharded load (sharding.ShardedLoad)
+    def needed_bins(self):
+        """(first_bin, count) of every channel's gathered bins, cyclic indices of the N-bin
+        spectrum: channel i reads bins (k - roll) mod N for k in [-B/2, B/2] (tuner.py:151-161)."""
+        n = int(self._input_bandwidth)
+        out = []
+        for ch in self._bounds:
+            roll = int(self._input_frequency - ch.center_frequency) % n
+            bw = int(ch.bandwidth)
+            out.append(((-(bw // 2) - roll) % n, bw + 1))
+        return out
+
+    def set_subband(self, x_lo, x_len):
+        """From now on ``load_subband`` hands the engine bins [x_lo, x_lo + x_len) (cyclic) of the
+        block's spectrum instead of ``load`` handing it the block (rebuilds the engine)."""
+        self._subband = None if x_lo is None else (int(x_lo), int(x_len))
+
+    def load_subband(self, spectrum):
+        """``Tuner.load`` for a sub-band computed elsewhere: a CUDA complex64 tensor holding bins
+        [x_lo, x_lo + x_len) of fft(block); it is read (not copied) by the following run calls."""
+        self._ensure_engine()
+        if self._subband is None:
+            raise RuntimeError("Tuner.set_subband must be called first")
+        if not (isinstance(spectrum, torch.Tensor) and spectrum.is_cuda and spectrum.dtype == torch.complex64
+                and spectrum.is_contiguous() and spectrum.numel() >= self._subband[1]):
+            raise ValueError("spectrum must be a contiguous CUDA complex64 tensor of at least x_len bins")
+        self._input_ref = spectrum
+        _native.check(_native.lib().rc_engine_load_subband(self._engine, spectrum.data_ptr()))
         self._serial += 1
 
     def _stage_input(self, input_signal):

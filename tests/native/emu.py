@@ -192,6 +192,22 @@ class Tuner:
         self.input_bandwidth = 0.0
         self._eng = None
         self._audio = None
+        self._subband = None
+
+    def needed_bins(self):
+        n = int(self.input_bandwidth)
+        return [((-(int(c.bandwidth) // 2) - int(self.input_frequency - c.center_frequency)) % n, int(c.bandwidth) + 1)
+                for c in self._bounds]
+
+    def set_subband(self, x_lo, x_len):
+        self._subband = (int(x_lo), int(x_len))
+
+    def load_subband(self, spectrum):
+        """rc_engine_load_subband: the engine reads `spectrum` (kept alive here) in place."""
+        if self._eng is None:
+            self._commit()
+        self._sub = _c64(spectrum)
+        _check(lib().rc_engine_load_subband(self._eng, _p(self._sub)))
 
     def channels(self):
         return self._bounds
@@ -223,6 +239,8 @@ class Tuner:
             idx = C.c_int()
             _check(lib().rc_engine_add_channel(self._eng, C.c_int64(roll), C.c_int64(int(ch.bandwidth)),
                                                C.c_int64(A), mode, C.c_double(tau), C.byref(idx)))
+        if self._subband is not None:
+            _check(lib().rc_engine_set_subband(self._eng, C.c_int64(self._subband[0]), C.c_int64(self._subband[1])))
         _check(lib().rc_engine_commit(self._eng))
         tot = C.c_int64()
         _check(lib().rc_engine_audio_floats(self._eng, C.byref(tot)))
@@ -260,4 +278,28 @@ def fft(x, sign=-1):
     x = _c64(np.atleast_2d(x))
     out = np.empty_like(x)
     _check(lib().rc_fft_c2c(0, C.c_int64(x.shape[1]), x.shape[0], sign, _p(x), _p(out), None))
+    return out
+
+
+class Fft:
+    """rc_fft_* (persistent plan) on the replay build."""
+
+    def __init__(self, n, batch=1):
+        self.n, self.batch = int(n), int(batch)
+        self._h = C.c_void_p()
+        _check(lib().rc_fft_create(0, C.c_int64(self.n), self.batch, C.byref(self._h)))
+
+    def __call__(self, x, sign=-1):
+        x = _c64(x)
+        out = np.empty_like(x)
+        _check(lib().rc_fft_exec(self._h, sign, _p(x), _p(out), None))
+        return out
+
+
+def subband_combine(pieces, n_input, k0_base):
+    """rc_subband_combine: pieces (G, P) complex64 -> bins (G, P)."""
+    pieces = _c64(pieces)
+    g, p = pieces.shape
+    out = np.empty_like(pieces)
+    _check(lib().rc_subband_combine(0, g, C.c_int64(p), C.c_int64(n_input), C.c_int64(k0_base), _p(pieces), _p(out), None))
     return out

@@ -105,3 +105,47 @@ def test_wide_tile_schedules_replay(emu, monkeypatch):
     assert np.array_equal(wide, narrow)               # same arithmetic, different tiling
     ref = np.fft.ifft(x.astype(np.complex128), axis=1) * n
     assert np.max(np.abs(wide - ref)) / np.sqrt(np.mean(np.abs(ref) ** 2)) < 3e-6
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_load_replay(emu, world):
+    """The native pieces of the sharded Tuner.load (rc_fft_exec on the commutator branches,
+    rc_subband_combine, an engine in sub-band mode) with the exchanges done by array slicing in one
+    process: every virtual rank's audio against the oracle, and its sub-band against a float64 FFT."""
+    import radiocore_oracle as oracle
+    from bench_support import synth
+    from radiocore.tools import sharding
+    N, B, A, C_ = 128_000, 16_000, 3_200, 8
+    offs = synth.tiling_centers(N, C_, B)
+    x = synth.wideband(N, offs, B, seed=77)
+    o = oracle.Tuner()
+    for off in offs:
+        o.add_channel(1e8 + off, B, oracle.MFM(B, A))
+    o.request_bandwidth(N)
+    o.load(x)
+    X64 = np.fft.fft(x.astype(np.complex128))
+    tuners, arcs = [], []
+    for r in range(world):
+        t = emu.Tuner()
+        sharding.shard_tuner(t, [1e8 + f for f in offs], B, lambda c: emu.MFM(B, A), 1e8, N, world, r)
+        arcs.append(sharding.covering_arc(t.needed_bins(), N))
+        t.set_subband(*arcs[-1])
+        tuners.append(t)
+    plan = sharding.SubbandPlan(N, world, arcs)
+    fft = emu.Fft(plan.m)
+    F = [fft(x[g::world]) for g in range(world)]                                   # local transforms
+    Y = [emu.subband_combine(np.stack([F[g][p * plan.p:(p + 1) * plan.p] for g in range(world)]), N, p * plan.p)
+         for p in range(world)]                                                    # exchange 1 + combine
+    for d in range(world):
+        sub = np.zeros(arcs[d][1] + 64, dtype=np.complex64)
+        for src in range(world):                                                   # exchange 2
+            for k1, j0, j1, pos in plan.runs(src, d):
+                sub[pos: pos + (j1 - j0)] = Y[src][k1, j0:j1]
+        want = X64[(arcs[d][0] + np.arange(arcs[d][1])) % N]
+        assert np.max(np.abs(sub[:arcs[d][1]] - want)) <= 3e-6 * np.sqrt(np.mean(np.abs(X64) ** 2)) * 10
+        tuners[d].load_subband(sub)
+        audio = tuners[d].run_all()
+        mine = list(sharding.channel_slice(C_, world, d))
+        for i, c in enumerate(mine):
+            ref = o.channels()[c].demodulator.run(o.run(c))
+            parity.assert_parity(audio[i], ref, f"world {world} rank {d} ch {c}")
