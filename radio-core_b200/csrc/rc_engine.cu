@@ -328,7 +328,9 @@ struct DemodBank {
         p.stage = d_stage; p.partial = d_partial;
         p.A = A; p.nch = nch; p.ntaps = 51; p.deemph = 1; p.dc_clip = 1;
         RC_API_CUDA(launch_epilogue(p, batch, st, taps), "epilogue");
-        std::swap(d_zi, d_zi_next);
+        // carried state: copied back rather than swapping the two pointers, so that a captured
+        // CUDA graph of the block (fixed kernel arguments) carries it correctly when replayed
+        RC_API_CUDA(dev_copy(d_zi, d_zi_next, (size_t)batch * nch * 50 * sizeof(double), cudaMemcpyDeviceToDevice, st), "zi carry");
         return RC_OK;
     }
 };
@@ -792,7 +794,7 @@ int rc_deemph_run(rc_deemph* d, const float* in, float* outp, void* stream) {
     p.stage = nullptr; p.partial = nullptr;
     p.A = d->size; p.nch = 1; p.ntaps = 51; p.deemph = 1; p.dc_clip = 0;
     RC_API_CUDA(launch_epilogue(p, 1, (cudaStream_t)stream, d->taps), "deemph");
-    std::swap(d->d_zi, d->d_zi_next);
+    RC_API_CUDA(dev_copy(d->d_zi, d->d_zi_next, 50 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "zi carry");
     return RC_OK;
 }
 

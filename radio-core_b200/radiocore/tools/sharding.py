@@ -271,15 +271,17 @@ class ShardedLoad:
                 w.wait()
 
     # ---- block interface
-    def post(self, x_branch) -> None:
-        """Start the load of the next block from this rank's branch x[rank::world] (M samples)."""
+    def post(self, x_branch, ready=None) -> None:
+        """Start the load of the next block from this rank's branch x[rank::world] (M samples).
+        ``ready``: optional CUDA event after which ``x_branch`` is valid (e.g. its host-to-device
+        copy on another stream); without it the branch is ordered after the caller's stream."""
         if len(self._pending) >= self._depth:
             raise RuntimeError("too many blocks in flight: take() before the next post()")
         if x_branch.numel() != self.plan.m:
             raise ValueError("the branch holds N / world_size samples")
         slot = self._slots[self._turn]
         self._turn = (self._turn + 1) % self._depth
-        done = self._k.begin(x_branch, slot)
+        done = self._k.begin(x_branch, slot, ready)
         self._k.fft(x_branch, self._F)
         self._exchange_pieces()
         self._k.combine(self._R, self._Y, self._rank * self.plan.p)
@@ -330,9 +332,11 @@ class _NativeKernels:
     def empty(self, n):
         return torch.empty(int(n), dtype=torch.complex64, device="cuda")
 
-    def begin(self, x_branch, slot):
+    def begin(self, x_branch, slot, ready=None):
         cur = torch.cuda.current_stream()
         self._stream.wait_stream(cur)                     # the producer of x_branch, and the previous readers of `slot`
+        if ready is not None:
+            self._stream.wait_event(ready)
         x_branch.record_stream(self._stream)
         self._ctx = torch.cuda.stream(self._stream)
         self._ctx.__enter__()

@@ -291,6 +291,48 @@ def test_config3_literal_block(rc):
     print("config3 literal worst rel err", worst)
 
 
+def test_config3_short_block(rc):
+    """Short-block variant of config 3: T = 1/32 s blocks, N = 8e6, 256 channels of
+    B*T = 31250 bins, FM to A*T = 1500 samples.  The reference is size-driven (tuner.py:155-157,
+    decimate.py:32-33), so the oracle instantiated in BIN UNITS -- Tuner.add_channel(f*T, bw*T),
+    FM(bw*T, 48e3*T) -- is the reference for this mode; every channel, two blocks, eager and
+    through the captured CUDA graph (Tuner.step)."""
+    import bench
+    N, C_, B, A = bench.WORKLOADS["cfg3-short"][:4]
+    g, o, offs = _pair(rc, N, B, A, C_, "FM")
+    g2, _, _ = _pair(rc, N, B, A, C_, "FM")
+    worst = 0.0
+    for blk in range(3):
+        x = bench.make_wideband_gpu(N, C_, B, 3 + 100 * blk, False, "cuda")[0]
+        g.load(x)
+        audio = g.run_all(numpy_output=True).copy()
+        stepped = g2.step(x, numpy_output=True).copy()          # block 0 eager, block 1 captured + replayed, block 2 replayed
+        assert np.array_equal(audio, stepped), f"graph replay differs, block {blk}"
+        if blk == 2:
+            continue
+        o.load(x.cpu().numpy())
+        for c, (off_c, size, nch) in enumerate(g.audio_slices()):
+            ref = o.channels()[c].demodulator.run(o.run(c))
+            worst = max(worst, parity.assert_parity(audio[off_c: off_c + size].reshape(size, 1), ref, f"short b{blk} ch{c}"))
+    print("config3 short-block worst rel err", worst)
+
+
+def test_graph_step_carries_state(rc):
+    """Tuner.step (one CUDA graph per block) == load + run_all for demodulators with carried
+    de-emphasis state (MFM, WBFM), four blocks."""
+    N, B, A, C_ = 2_000_000, 250_000, 48_000, 8
+    offs = synth.tiling_centers(N, C_, B)
+    for kind in ("MFM", "WBFM"):
+        a, _, _ = _pair(rc, N, B, A, C_, kind)
+        b, _, _ = _pair(rc, N, B, A, C_, kind)
+        for blk in range(4):
+            x = synth.wideband(N, offs, B, seed=17, stereo=kind == "WBFM", block=blk)
+            a.load(x)
+            want = a.run_all(numpy_output=True).copy()
+            got = b.step(x, numpy_output=True).copy()
+            assert np.array_equal(want, got), (kind, blk)
+
+
 def test_config5_one_gpu_slice(rc):
     """BASELINE configs[4]: N = 1e9, 2048 x 250 kHz FM channels, 256 per GPU.  One GPU's slice
     (rank 3 of 8: channels 768..1023, band plan of the full list) on the full 1 G-sample block;

@@ -105,7 +105,7 @@ class _NumpyKernels:
     def empty(self, count):
         return torch.zeros(int(count), dtype=torch.complex128)
 
-    def begin(self, x, slot):
+    def begin(self, x, slot, ready=None):
         return None
 
     def end(self, token):
