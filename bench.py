@@ -476,6 +476,28 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
     while load.in_flight():
         load.take()
     torch.cuda.synchronize()
+    # decomposition, outside the timed value: the load pipeline on its own (phases on the side stream,
+    # nothing else running), then the channel stage on its own
+    load.phase_events = []
+    sub = None
+    for _ in range(3):
+        load.post(branch)
+        sub = load.take()
+        torch.cuda.synchronize()
+    phases = load.phase_ms()
+    load.phase_events = None
+    tuner.load_subband(sub)
+    tuner.run_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(3):
+        tuner.run_all()
+    ev1.record()
+    torch.cuda.synchronize()
+    res["decomposition"] = {"transport": load.transport, "load_pipeline_ms": {k: round(v, 4) for k, v in phases.items()},
+                            "load_pipeline_total_ms": round(sum(phases.values()), 4),
+                            "channel_stage_ms": round(ev0.elapsed_time(ev1) / 3, 4),
+                            "note": "each measured alone on rank 0; in the timed step block k+1's load pipeline overlaps block k's channel stage"}
     del load, tuner
     torch.cuda.empty_cache()
     return res
@@ -635,6 +657,8 @@ def run_b200(args, rank, world, local_rank):
             "kernels": table, "clocks": res["clocks"]}
     if "nvlink_bytes_sent_per_rank_per_step" in res:
         line["run"]["nvlink_bytes_sent_per_rank_per_step"] = res["nvlink_bytes_sent_per_rank_per_step"]
+    if "decomposition" in res:
+        line["run"]["decomposition"] = res["decomposition"]
     if "e2e" in res:
         e = res["e2e"]
         line["e2e"] = {"value": N * streams * steps / e["t"] / 1e6, "unit": UNIT,

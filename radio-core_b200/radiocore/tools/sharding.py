@@ -9,6 +9,7 @@ stream.  There is no reduction and no gather of audio: every rank emits its own 
 Works on any ``torch.distributed`` backend (NCCL on the GPUs, gloo in the CPU tests).
 """
 import collections
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -217,12 +218,32 @@ class ShardedLoad:
         tuner.set_subband(self.x_lo, self.x_len)
         self._k = kernels if kernels is not None else _NativeKernels(self.plan, self._rank)
         k, plan = self._k, self.plan
-        self._F = k.empty(plan.m)                                   # F_g, natural order: piece p = [p*P, (p+1)*P)
-        self._R = k.empty(plan.m)                                   # [G][P]: piece `rank` of every F_g
-        self._Y = k.empty(plan.m)                                   # [G][P]: bins k1*M + rank*P + j
-        pad = 1 << 16                                               # the gather's tensor map describes whole rows past x_len
-        self._slots = [k.empty(self.x_len + pad) for _ in range(max(2, depth))]
         self._depth = max(2, depth)
+        pad = 1 << 16                                               # the gather's tensor map describes whole rows past x_len
+        slot_len = max(b for _, b in arcs) + pad
+        self._F = k.empty(plan.m)                                   # F_g, natural order: piece p = [p*P, (p+1)*P)
+        self._Y = k.empty(plan.m)                                   # [G][P]: bins k1*M + rank*P + j
+        # Transport of the two exchanges.  "peer": the receive buffers (R and the sub-band slots) live in
+        # symmetric memory mapped into every rank (torch.distributed._symmetric_memory); a rank PUSHES its
+        # pieces / runs straight into the peers' buffers with device-to-device copies over NVLink and a
+        # stream-ordered barrier closes each exchange -- no NCCL send/recv kernels competing for SMs, and
+        # the copies run at link rate.  "collective": torch.distributed all-to-all / batched send-recv
+        # (NCCL or gloo) into private buffers -- the portable path the CPU tests exercise.
+        self._peer = None
+        want = os.environ.get("RC_SHARD_TRANSPORT", "peer" if kernels is None else "collective")
+        if want == "peer" and self._world > 1:
+            try:
+                self._peer = _PeerBuffers(plan.m, slot_len, self._depth, self._world, self._rank, group)
+            except Exception as exc:                                # pragma: no cover - depends on the box
+                import warnings
+                warnings.warn(f"radiocore: symmetric-memory transport unavailable ({exc!r}); using NCCL send/recv")
+        self.transport = "peer" if self._peer is not None else "collective"
+        if self._peer is not None:
+            self._R, self._slots = self._peer.R, self._peer.slots
+        else:
+            self._R = k.empty(plan.m)                               # [G][P]: piece `rank` of every F_g
+            self._slots = [k.empty(slot_len) for _ in range(self._depth)]
+        self.phase_events = None                                    # set to [] to record (name, event) pairs per post()
         self._turn = 0
         self._pending = collections.deque()
         self._send = [plan.runs(self._rank, d) for d in range(self._world)]
@@ -234,6 +255,13 @@ class ShardedLoad:
         """R[g] = F_g[rank*P : (rank+1)*P] from every rank g (equal-split all-to-all)."""
         if self._world == 1:
             self._R.copy_(self._F)
+            return
+        if self._peer is not None:
+            p, g = self.plan.p, self._rank
+            for step in range(self._world):                          # start with the neighbour: spread the traffic
+                d = (g + step) % self._world
+                self._peer.R_of(d)[g * p:(g + 1) * p].copy_(self._F[d * p:(d + 1) * p], non_blocking=True)
+            self._peer.barrier(0)
             return
         out, inp = _as_real(self._R), _as_real(self._F)
         if dist.get_backend(self._group) == "nccl":
@@ -252,6 +280,15 @@ class ShardedLoad:
     def _exchange_bins(self, slot):
         """Exchange 2: the runs of SubbandPlan straight from Y into the destination sub-bands."""
         p = self.plan.p
+        if self._peer is not None:
+            idx = next(i for i, t in enumerate(self._slots) if t is slot)
+            for step in range(self._world):
+                d = (self._rank + step) % self._world
+                dst = self._peer.slot_of(d, idx)
+                for k1, j0, j1, pos in self._send[d]:
+                    dst[pos: pos + (j1 - j0)].copy_(self._Y[k1 * p + j0: k1 * p + j1], non_blocking=True)
+            self._peer.barrier(1)
+            return
         Y, X = _as_real(self._Y), _as_real(slot)
         ops = []
         for d in range(self._world):
@@ -282,11 +319,30 @@ class ShardedLoad:
         slot = self._slots[self._turn]
         self._turn = (self._turn + 1) % self._depth
         done = self._k.begin(x_branch, slot, ready)
+        self._mark("begin")
         self._k.fft(x_branch, self._F)
+        self._mark("local_fft")
         self._exchange_pieces()
+        self._mark("exchange_pieces")
         self._k.combine(self._R, self._Y, self._rank * self.plan.p)
+        self._mark("combine")
         self._exchange_bins(slot)
+        self._mark("exchange_bins")
         self._pending.append((slot, self._k.end(done)))
+
+    def _mark(self, name):
+        if self.phase_events is not None and hasattr(self._k, "mark"):
+            self.phase_events.append((name, self._k.mark()))
+
+    def phase_ms(self):
+        """Mean device milliseconds of each phase of post() over the recorded blocks (side stream)."""
+        ev, out, count = self.phase_events or [], {}, {}
+        for (n0, e0), (n1, e1) in zip(ev, ev[1:]):
+            if n1 == "begin":
+                continue
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+            count[n1] = count.get(n1, 0) + 1
+        return {k: v / count[k] for k, v in out.items()}
 
     def take(self):
         """Sub-band of the oldest posted block (bins [x_lo, x_lo + x_len)), ordered after its arrival."""
@@ -352,6 +408,11 @@ class _NativeKernels:
         self._native.check(self._native.lib().rc_subband_combine(
             self._dev, p.world, p.p, p.n, int(k0_base), pieces.data_ptr(), bins.data_ptr(), self._stream.cuda_stream))
 
+    def mark(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(self._stream)
+        return ev
+
     def end(self, _):
         ev = torch.cuda.Event()
         ev.record(self._stream)
@@ -361,3 +422,33 @@ class _NativeKernels:
 
     def wait(self, ev, slot):
         torch.cuda.current_stream().wait_event(ev)
+
+
+class _PeerBuffers:
+    """Receive buffers of ShardedLoad in symmetric memory: one allocation per rank holding R ([G][P]
+    pieces) and the sub-band slots, mapped into every rank of the group, plus the stream-ordered
+    barrier of the mapping (signal pads in the same symmetric allocation)."""
+
+    def __init__(self, m, slot_len, depth, world, rank, group):
+        import torch.distributed._symmetric_memory as symm
+        self._m, self._slot_len, self._depth = int(m), int(slot_len), int(depth)
+        total = 2 * (self._m + self._depth * self._slot_len)          # float32 words (complex64 = 2)
+        self._buf = symm.empty(total, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self._hdl = symm.rendezvous(self._buf, group if group is not None else dist.group.WORLD)
+        self._views = [self._buf if r == rank else self._hdl.get_buffer(r, (total,), torch.float32) for r in range(world)]
+        self.R = self._complex(self._buf, 0, self._m)
+        self.slots = [self._complex(self._buf, self._m + i * self._slot_len, self._slot_len) for i in range(depth)]
+        self.ptrs = list(self._hdl.buffer_ptrs)                       # peer base addresses (for kernels that store remotely)
+
+    @staticmethod
+    def _complex(buf, first, count):
+        return torch.view_as_complex(buf[2 * first: 2 * (first + count)].view(count, 2))
+
+    def R_of(self, r):
+        return self._complex(self._views[r], 0, self._m)
+
+    def slot_of(self, r, i):
+        return self._complex(self._views[r], self._m + i * self._slot_len, self._slot_len)
+
+    def barrier(self, channel):
+        self._hdl.barrier(channel=channel)

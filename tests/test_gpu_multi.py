@@ -60,5 +60,9 @@ def test_one_stream_channel_shards(tmp_path, world):
             if b == 0:
                 lo, length = g["arc"]
                 sub = X[(lo + np.arange(length)) % N]
-                assert np.max(np.abs(g["subband"] - sub)) <= 5e-6 * np.sqrt(np.mean(np.abs(X) ** 2))
+                # fp32 transform: rounding noise ~ eps * rms over all bins, plus eps * |X_k| on the strong
+                # lines of the FM stations (twiddle rounding scales with the bin itself)
+                err = np.abs(g["subband"] - sub)
+                assert np.sqrt(np.mean(err ** 2)) <= 2e-6 * np.sqrt(np.mean(np.abs(X) ** 2))
+                assert np.max(err) <= 2e-6 * np.max(np.abs(X)) + 5e-6 * np.sqrt(np.mean(np.abs(X) ** 2))
     print(f"world {world}: sharded-load audio worst rel err {worst:.2e}")
