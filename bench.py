@@ -491,6 +491,7 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(3):
+        tuner.load_subband(sub)
         tuner.run_all()
     ev1.record()
     torch.cuda.synchronize()

@@ -375,7 +375,7 @@ class _NativeKernels:
         self._fft = C.c_void_p()
         _native.check(_native.lib().rc_fft_create(self._dev, plan.m, 1, C.byref(self._fft)))
         self._ctx = None
-        self._readers = {}            # sub-band buffer -> event of the last channel kernels that read it
+        self._fft_done = None
 
     def __del__(self):
         h, self._fft = getattr(self, "_fft", None), None
@@ -402,6 +402,8 @@ class _NativeKernels:
         x = x.contiguous()
         self._native.check(self._native.lib().rc_fft_exec(self._fft, -1, x.data_ptr(), out.data_ptr(),
                                                           self._stream.cuda_stream))
+        self._fft_done = torch.cuda.Event()
+        self._fft_done.record(self._stream)
 
     def combine(self, pieces, bins, k0_base):
         p = self._plan
@@ -421,7 +423,13 @@ class _NativeKernels:
         return ev
 
     def wait(self, ev, slot):
-        torch.cuda.current_stream().wait_event(ev)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        # Take turns on the SMs: the caller's channel kernels for this block start once the local FFT
+        # of the block posted after it has finished, so they run beside that block's NVLink copies
+        # (copy engines, no SMs) instead of sharing HBM bandwidth with its FFT passes.
+        if self._fft_done is not None:
+            cur.wait_event(self._fft_done)
 
 
 class _PeerBuffers:
