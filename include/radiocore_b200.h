@@ -83,11 +83,22 @@ int rc_engine_load_subband(rc_engine* e, const void* spectrum_dev);
 int rc_subband_combine(int device, int n_ranks, int64_t piece_len, int64_t n_input, int64_t k0_base,
                        const void* pieces_dev /* [G][P] complex64 */, void* bins_dev /* [G][P] */, void* stream);
 
+/* The same two steps with the exchanges fused into their stores (peer-mapped destination buffers,
+ * e.g. torch.distributed._symmetric_memory): rc_fft_exec_scatter writes output element i to
+ * piece_bases[i / piece_len][i % piece_len] (batch 1, piece_len even), rc_subband_combine_scatter
+ * writes bin (k1, j) of the combine to seg.dst[j - seg.j_lo] for every segment with seg.k1 == k1 and
+ * j in [j_lo, j_hi) (at most 4 segments per k1).  Destinations may be NVLink peers' memory. */
+typedef struct { int32_t k1; int32_t reserved; int64_t j_lo, j_hi; void* dst; } rc_scatter_seg;
+int rc_subband_combine_scatter(int device, int n_ranks, int64_t piece_len, int64_t n_input, int64_t k0_base,
+                               const void* pieces_dev, const rc_scatter_seg* segs, int n_segs, void* stream);
+
 /* ---- persistent complex FFT plan (batched, in != out): the local transform of the sharded load */
 typedef struct rc_fft rc_fft;
 int rc_fft_create(int device, int64_t n, int batch, rc_fft** out);
 int rc_fft_destroy(rc_fft* f);
 int rc_fft_exec(rc_fft* f, int sign, const void* in_dev, void* out_dev, void* stream);
+int rc_fft_exec_scatter(rc_fft* f, int sign, const void* in_dev, void* const* piece_bases, int n_pieces,
+                        int64_t piece_len, void* stream);
 
 /* ---- standalone demodulators: FM.run / MFM.run / WBFM.run on `batch` blocks */
 typedef struct rc_demod rc_demod;

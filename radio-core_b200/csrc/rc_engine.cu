@@ -18,6 +18,10 @@
 #include "../../include/radiocore_b200.h"
 #include "rc_exec.cuh"
 
+#ifndef RC_EMULATE
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges around the block-level entry points
+#endif
+
 namespace rc {
 
 static thread_local std::string g_last_error;
@@ -34,6 +38,17 @@ static int cuda_fail(cudaError_t e, const char* where) {
         cudaError_t _e = (expr);                          \
         if (_e != cudaSuccess) return cuda_fail(_e, where); \
     } while (0)
+
+// NVTX range for the lifetime of an API call (visible in Nsight Systems / ncu --nvtx): the
+// reference has no profiler hooks; these mark Tuner.load and the channel loop.
+struct NvtxRange {
+#ifndef RC_EMULATE
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+#else
+    explicit NvtxRange(const char*) {}
+#endif
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -521,6 +536,7 @@ int rc_engine_load(rc_engine* e, const void* iq_dev, void* stream) {
     if (e->subband) return fail(RC_ERR_STATE, "engine: sub-band mode takes rc_engine_load_subband");
     if (!iq_dev) return fail(RC_ERR_INVALID, "engine: null input");
     DeviceGuard g(e->device);
+    NvtxRange range("radiocore.Tuner.load");
     cudaStream_t st = (cudaStream_t)stream;
     RC_API_CUDA((fft_exec<-1>(e->planN, 1, LoadC64{(const float2*)iq_dev, e->N}, StoreC64{e->X, e->N, 1.0f},
                               e->wN0, e->wN1, st, "tuner.load_fft")), "tuner load fft");
@@ -560,6 +576,7 @@ int rc_engine_run(rc_engine* e, float* audio_dev, void* stream) {
     if (!e || !e->committed || !e->loaded) return fail(RC_ERR_STATE, "engine: run before load");
     if (!audio_dev && e->audio_total > 0) return fail(RC_ERR_INVALID, "engine: null output");
     DeviceGuard g(e->device);
+    NvtxRange range("radiocore.Tuner.run+demodulators");
     cudaStream_t st = (cudaStream_t)stream;
     for (auto& bp : e->banks) {
         auto& bk = *bp;
@@ -969,6 +986,38 @@ int rc_subband_combine(int device, int n_ranks, int64_t piece_len, int64_t n_inp
     return RC_OK;
 }
 
+int rc_subband_combine_scatter(int device, int n_ranks, int64_t piece_len, int64_t n_input, int64_t k0_base,
+                               const void* pieces_dev, const rc_scatter_seg* segs, int n_segs, void* stream) {
+    if (!pieces_dev || !segs || n_segs < 1 || piece_len < 1 || n_input < 1 || k0_base < 0)
+        return fail(RC_ERR_INVALID, "subband_combine_scatter: bad argument");
+    ScatterTable tab;
+    memset(&tab, 0, sizeof(tab));
+    for (int i = 0; i < n_segs; i++) {
+        const rc_scatter_seg& sg = segs[i];
+        if (sg.k1 < 0 || sg.k1 >= n_ranks || sg.k1 >= kMaxRanks || !sg.dst || sg.j_lo < 0 || sg.j_hi > piece_len || sg.j_lo >= sg.j_hi)
+            return fail(RC_ERR_INVALID, "subband_combine_scatter: bad segment");
+        int& n = tab.n[sg.k1];
+        if (n >= kScatterSegs) return fail(RC_ERR_UNSUPPORTED, "subband_combine_scatter: more than 4 segments for one k1");
+        tab.lo[sg.k1][n] = sg.j_lo; tab.hi[sg.k1][n] = sg.j_hi; tab.dst[sg.k1][n] = (float2*)sg.dst;
+        n++;
+    }
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double bytes = 16.0 * (double)piece_len * n_ranks;
+    const float2* F = (const float2*)pieces_dev;
+    const double m2n = -2.0 / (double)n_input;
+    cudaError_t err;
+    switch (n_ranks) {
+        case 2: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<2>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes); break;
+        case 4: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<4>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes); break;
+        case 8: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<8>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes); break;
+        case 16: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<16>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes); break;
+        default: return fail(RC_ERR_UNSUPPORTED, "subband_combine_scatter: 2, 4, 8 or 16 ranks");
+    }
+    RC_API_CUDA(err, "subband combine scatter");
+    return RC_OK;
+}
+
 struct rc_fft {
     int device = 0, batch = 1;
     long long n = 0;
@@ -1004,6 +1053,28 @@ int rc_fft_exec(rc_fft* f, int sign, const void* in, void* outp, void* stream) {
     if (sign < 0) e = fft_exec<-1>(f->plan, f->batch, LoadC64{(const float2*)in, f->n}, StoreC64{(float2*)outp, f->n, 1.0f}, f->w0, f->w1, st, "tuner.local_fft");
     else e = fft_exec<+1>(f->plan, f->batch, LoadC64{(const float2*)in, f->n}, StoreC64{(float2*)outp, f->n, 1.0f}, f->w0, f->w1, st, "tuner.local_fft");
     RC_API_CUDA(e, "fft exec");
+    return RC_OK;
+}
+
+int rc_fft_exec_scatter(rc_fft* f, int sign, const void* in, void* const* piece_bases, int n_pieces,
+                        int64_t piece_len, void* stream) {
+    if (!f || !in || !piece_bases || (sign != 1 && sign != -1)) return fail(RC_ERR_INVALID, "fft: bad argument");
+    if (f->batch != 1 || n_pieces < 1 || n_pieces > kMaxRanks || piece_len < 2 || (piece_len & 1) ||
+        (long long)n_pieces * piece_len != f->n || f->n >= (1LL << 31))
+        return fail(RC_ERR_UNSUPPORTED, "fft scatter: batch 1, <= 16 even pieces that tile the transform");
+    StoreScatterC64 st_op;
+    memset(&st_op, 0, sizeof(st_op));
+    for (int i = 0; i < n_pieces; i++) {
+        if (!piece_bases[i] || (((size_t)piece_bases[i]) & 15)) return fail(RC_ERR_INVALID, "fft scatter: piece bases must be 16-byte aligned");
+        st_op.base[i] = (float2*)piece_bases[i];
+    }
+    st_op.P = (unsigned)piece_len;
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (sign < 0) e = fft_exec<-1>(f->plan, 1, LoadC64{(const float2*)in, f->n}, st_op, f->w0, f->w1, st, "tuner.local_fft");
+    else e = fft_exec<+1>(f->plan, 1, LoadC64{(const float2*)in, f->n}, st_op, f->w0, f->w1, st, "tuner.local_fft");
+    RC_API_CUDA(e, "fft exec scatter");
     return RC_OK;
 }
 

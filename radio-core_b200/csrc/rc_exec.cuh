@@ -10,7 +10,7 @@ namespace rc {
 
 // ---- the functor kinds the register-radix kernels (rc_fft3.cuh) are compiled for ----
 enum { kLdC64 = 0, kLdGather = 1, kLdDisc = 2, kLdTma = 3, kLdAng = 4, kLdGatherTma = 5, kLdAngTma = 6 };
-enum { kStC64 = 0, kStLmr = 1, kStWin = 2, kStAng = 3 };
+enum { kStC64 = 0, kStLmr = 1, kStWin = 2, kStAng = 3, kStScatter = 4 };
 
 struct LoadAny {
     int kind;
@@ -28,6 +28,7 @@ struct StoreAny {
     StoreLmrPacked lmr;
     StoreC64Win win;
     StoreAngle angle;
+    StoreScatterC64 scatter;
 };
 
 template <class L> struct V3LoadOk { static constexpr bool value = false; };
@@ -40,6 +41,7 @@ template <> struct V3StoreOk<StoreC64> { static constexpr bool value = true; };
 template <> struct V3StoreOk<StoreLmrPacked> { static constexpr bool value = true; };
 template <> struct V3StoreOk<StoreC64Win> { static constexpr bool value = true; };
 template <> struct V3StoreOk<StoreAngle> { static constexpr bool value = true; };
+template <> struct V3StoreOk<StoreScatterC64> { static constexpr bool value = true; };
 
 // A complex64 source becomes a TMA tile load when its layout allows a tensor map.
 inline LoadAny to_any(const LoadC64& l, const FftPass& P, int batch) {
@@ -107,6 +109,7 @@ inline LoadAny to_any(const LoadAnglePacked& l, const FftPass& P, int batch) {
     return a;
 }
 inline StoreAny to_any(const StoreAngle& s) { StoreAny a{}; a.kind = kStAng; a.angle = s; return a; }
+inline StoreAny to_any(const StoreScatterC64& s) { StoreAny a{}; a.kind = kStScatter; a.scatter = s; return a; }
 inline StoreAny to_any(const StoreC64Win& s) { StoreAny a{}; a.kind = kStWin; a.win = s; return a; }
 
 // Defined in rc_fft3_g<k>.cu (schedule ids with id % kV3Groups == k).

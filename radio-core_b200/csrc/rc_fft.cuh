@@ -345,6 +345,25 @@ struct StoreC64Win {
     }
 };
 
+// complex64 store that SCATTERS the output over up to kMaxRanks destination buffers: element i goes
+// to base[i / P][i % P].  The bases are device pointers of this GPU *or of its NVLink peers* (mapped
+// symmetric memory): the last pass of the local transform of the sharded Tuner.load writes every
+// piece straight into the rank that combines it -- the first exchange of radiocore/tools/sharding.py
+// is the store of the FFT itself, not a separate copy.  P is even (pairs never straddle two pieces).
+constexpr int kMaxRanks = 16;
+struct StoreScatterC64 {
+    float2* base[kMaxRanks];
+    unsigned P;
+    RC_HD void operator()(int, long long i, float2 v) const {
+        const unsigned u = (unsigned)i, p = u / P;
+        base[p][u - p * P] = v;
+    }
+    RC_HD void pair(int, long long i, float2 v, float2 w) const {
+        const unsigned u = (unsigned)i, p = u / P;
+        stg4(base[p] + (u - p * P), v, w);
+    }
+};
+
 // ------------------------------------------------------------- pass phases
 template <class LoadOp, int SIGN>
 RC_HD void fft_pass_load(float2* sm, const FftPass& P, const LoadOp& ld, int batch,

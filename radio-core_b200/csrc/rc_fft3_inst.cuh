@@ -155,6 +155,7 @@ v3_later_kernel(const FftPass P, const LoadAny ld, const StoreAny st, const __gr
     if (st.kind == kStLmr) v3_last_direct<S, SIGN>(tile, P, st.lmr, batch, j0, tid);
     else if (st.kind == kStWin) v3_last_direct<S, SIGN>(tile, P, st.win, batch, j0, tid);
     else if (st.kind == kStAng) v3_last_direct<S, SIGN>(tile, P, st.angle, batch, j0, tid);
+    else if (st.kind == kStScatter) v3_last_direct<S, SIGN>(tile, P, st.scatter, batch, j0, tid);
     else v3_last_direct<S, SIGN>(tile, P, st.c64, batch, j0, tid);
 }
 
@@ -255,6 +256,7 @@ cudaError_t v3_run_later(const FftPass& P, const LoadAny& ld, const StoreAny& st
                 if (st.kind == kStLmr) v3_last_direct<S, SIGN>(tile, P, st.lmr, b, j0, tid);
                 else if (st.kind == kStWin) v3_last_direct<S, SIGN>(tile, P, st.win, b, j0, tid);
                 else if (st.kind == kStAng) v3_last_direct<S, SIGN>(tile, P, st.angle, b, j0, tid);
+                else if (st.kind == kStScatter) v3_last_direct<S, SIGN>(tile, P, st.scatter, b, j0, tid);
                 else v3_last_direct<S, SIGN>(tile, P, st.c64, b, j0, tid);
             }
         }

@@ -588,6 +588,49 @@ struct SubbandCombineEw {
     }
 };
 
+// The same combine with the second exchange fused into its stores: bin k0 + M k1 is written
+// straight into the sub-band buffer of every rank whose channels read it -- this GPU's or an NVLink
+// peer's (mapped symmetric memory) -- instead of into a local array that is copied afterwards.
+// tab: per k1 up to kScatterSegs segments [lo, hi) of j with the address of the segment's first bin.
+constexpr int kScatterSegs = 4;
+struct ScatterTable {
+    int n[kMaxRanks];
+    long long lo[kMaxRanks][kScatterSegs], hi[kMaxRanks][kScatterSegs];
+    float2* dst[kMaxRanks][kScatterSegs];
+};
+template <int G>
+struct SubbandCombineScatterEw {
+    const float2* F;      // [G][P]
+    long long P, k0_base;
+    double minus_two_over_n;
+    ScatterTable tab;
+    RC_HD void operator()(int, long long j) const {
+        float2 v[G];
+        double sn, cs;
+        const double th = (double)(k0_base + j) * minus_two_over_n;
+#ifdef __CUDA_ARCH__
+        sincospi(th, &sn, &cs);
+#else
+        sn = sin(kPi * th); cs = cos(kPi * th);
+#endif
+        const double2 w1 = make_double2(cs, sn);
+        double2 w = w1;
+        v[0] = ldg(F + j);
+#pragma unroll
+        for (int g = 1; g < G; g++) {
+            v[g] = cmul(ldg(F + (long long)g * P + j), make_float2((float)w.x, (float)w.y));
+            if (g + 1 < G) w = cmul64(w, w1);
+        }
+        Dft<G, -1>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < G; k1++) {
+#pragma unroll
+            for (int sgm = 0; sgm < kScatterSegs; sgm++)
+                if (sgm < tab.n[k1] && j >= tab.lo[k1][sgm] && j < tab.hi[k1][sgm]) tab.dst[k1][sgm][j - tab.lo[k1][sgm]] = v[k1];
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------
 // Zero-phase FIR (bandpass.py:72 filtfilt(b, 1, x), padtype 'odd').
 // With an FIR the lfilter_zi start-up terms only touch the first len(b)-1

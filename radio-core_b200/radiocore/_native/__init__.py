@@ -37,6 +37,8 @@ _SIGNATURES = {
     "rc_fft_create": ([_int, _i64, _int, _pp], _int),
     "rc_fft_destroy": ([_vp], _int),
     "rc_fft_exec": ([_vp, _int, _vp, _vp, _vp], _int),
+    "rc_fft_exec_scatter": ([_vp, _int, _vp, C.POINTER(C.c_void_p), _int, _i64, _vp], _int),
+    "rc_subband_combine_scatter": ([_int, _int, _i64, _i64, _i64, _vp, _vp, _int, _vp], _int),
     "rc_demod_create": ([_int, _int, _i64, _i64, _dbl, _int, _pp], _int),
     "rc_demod_destroy": ([_vp], _int),
     "rc_demod_run": ([_vp, _vp, _fp, _vp], _int),
@@ -64,6 +66,13 @@ _SIGNATURES = {
     "rc_profile_report": ([C.c_char_p, _int], _int),
     "rc_fft_c2c": ([_int, _i64, _int, _int, _vp, _vp, _vp], _int),
 }
+
+
+
+class ScatterSeg(C.Structure):
+    """rc_scatter_seg of include/radiocore_b200.h."""
+    _fields_ = [("k1", C.c_int32), ("reserved", C.c_int32), ("j_lo", C.c_int64), ("j_hi", C.c_int64), ("dst", C.c_void_p)]
+
 
 EXPORTED_SYMBOLS = ["rc_last_error"] + sorted(_SIGNATURES)
 

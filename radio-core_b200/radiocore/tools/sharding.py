@@ -244,6 +244,23 @@ class ShardedLoad:
             self._R = k.empty(plan.m)                               # [G][P]: piece `rank` of every F_g
             self._slots = [k.empty(slot_len) for _ in range(self._depth)]
         self.phase_events = None                                    # set to [] to record (name, event) pairs per post()
+        # With peer-mapped buffers the two exchanges can be the STORES of the kernels themselves: the
+        # last pass of the local FFT scatters each piece into the rank that combines it, and the combine
+        # writes every bin into the sub-band of the rank(s) that read it -- compute and NVLink transfer in
+        # one kernel each, a barrier after each, no staging arrays and no copies.  RC_SHARD_FUSED=0 keeps
+        # the kernels local and pushes with device-to-device copies instead.
+        self.fused = (self._peer is not None and hasattr(k, "fft_scatter") and plan.p % 2 == 0
+                      and os.environ.get("RC_SHARD_FUSED", "1") != "0")
+        if self.fused:
+            g, p8 = self._rank, 8 * plan.p
+            self._piece_bases = [self._peer.ptrs[d] + self._peer.r_offset_bytes + g * p8 for d in range(self._world)]
+            self._segs = []
+            for idx in range(self._depth):
+                segs = []
+                for d in range(self._world):
+                    base = self._peer.ptrs[d] + self._peer.slot_offset_bytes(idx)
+                    segs += [(k1, j0, j1, base + 8 * pos) for k1, j0, j1, pos in self._send[d]]
+                self._segs.append(k.make_segments(segs))
         self._turn = 0
         self._pending = collections.deque()
         self._send = [plan.runs(self._rank, d) for d in range(self._world)]
@@ -320,14 +337,25 @@ class ShardedLoad:
         self._turn = (self._turn + 1) % self._depth
         done = self._k.begin(x_branch, slot, ready)
         self._mark("begin")
-        self._k.fft(x_branch, self._F)
-        self._mark("local_fft")
-        self._exchange_pieces()
-        self._mark("exchange_pieces")
-        self._k.combine(self._R, self._Y, self._rank * self.plan.p)
-        self._mark("combine")
-        self._exchange_bins(slot)
-        self._mark("exchange_bins")
+        if self.fused:
+            idx = next(i for i, t in enumerate(self._slots) if t is slot)
+            self._k.fft_scatter(x_branch, self._piece_bases)
+            self._mark("local_fft+scatter")
+            self._peer.barrier(0)
+            self._mark("barrier_pieces")
+            self._k.combine_scatter(self._R, self._rank * self.plan.p, self._segs[idx])
+            self._mark("combine+scatter")
+            self._peer.barrier(1)
+            self._mark("barrier_bins")
+        else:
+            self._k.fft(x_branch, self._F)
+            self._mark("local_fft")
+            self._exchange_pieces()
+            self._mark("exchange_pieces")
+            self._k.combine(self._R, self._Y, self._rank * self.plan.p)
+            self._mark("combine")
+            self._exchange_bins(slot)
+            self._mark("exchange_bins")
         self._pending.append((slot, self._k.end(done)))
 
     def _mark(self, name):
@@ -405,6 +433,26 @@ class _NativeKernels:
         self._fft_done = torch.cuda.Event()
         self._fft_done.record(self._stream)
 
+    def fft_scatter(self, x, piece_bases):
+        C = self._C
+        x = x.contiguous()
+        arr = (C.c_void_p * len(piece_bases))(*piece_bases)
+        self._native.check(self._native.lib().rc_fft_exec_scatter(
+            self._fft, -1, x.data_ptr(), arr, len(piece_bases), self._plan.p, self._stream.cuda_stream))
+        self._fft_done = torch.cuda.Event()
+        self._fft_done.record(self._stream)
+
+    def make_segments(self, segs):
+        arr = (self._native.ScatterSeg * len(segs))()
+        for a, (k1, j0, j1, dst) in zip(arr, segs):
+            a.k1, a.reserved, a.j_lo, a.j_hi, a.dst = k1, 0, j0, j1, dst
+        return arr
+
+    def combine_scatter(self, pieces, k0_base, segs):
+        p = self._plan
+        self._native.check(self._native.lib().rc_subband_combine_scatter(
+            self._dev, p.world, p.p, p.n, int(k0_base), pieces.data_ptr(), segs, len(segs), self._stream.cuda_stream))
+
     def combine(self, pieces, bins, k0_base):
         p = self._plan
         self._native.check(self._native.lib().rc_subband_combine(
@@ -451,6 +499,13 @@ class _PeerBuffers:
     @staticmethod
     def _complex(buf, first, count):
         return torch.view_as_complex(buf[2 * first: 2 * (first + count)].view(count, 2))
+
+    @property
+    def r_offset_bytes(self):
+        return 0
+
+    def slot_offset_bytes(self, i):
+        return 8 * (self._m + i * self._slot_len)
 
     def R_of(self, r):
         return self._complex(self._views[r], 0, self._m)

@@ -59,20 +59,31 @@ def run(rank, world, port, out_dir, kind="MFM"):
             tb.load(feed.take())
             out[("bcast", b)] = slice_of(tb, tb.run_all(numpy_output=True), range(len(mine))).copy()
 
-        ts = radiocore.Tuner(cuda=True)
-        sharding.shard_tuner(ts, centers, B, make, F0, N, world, rank)
-        load = sharding.ShardedLoad(ts)
-        out["arc"] = (load.x_lo, load.x_len)
         branches = [x[rank::world].contiguous() for x in blocks]
-        load.post(branches[0])
-        for b in range(BLOCKS):
-            if b + 1 < BLOCKS:
-                load.post(branches[b + 1])
-            sub = load.take()
-            ts.load_subband(sub)
-            out[("sharded", b)] = slice_of(ts, ts.run_all(numpy_output=True), range(len(mine))).copy()
-            if b == 0:
-                out["subband"] = sub[:load.x_len].cpu().numpy()
+        # default: peer-mapped buffers, exchanges fused into the kernels' stores; then the same with
+        # device-to-device copies (RC_SHARD_FUSED=0) and over NCCL (RC_SHARD_TRANSPORT=collective)
+        for tag, env in (("sharded", {}), ("sharded_copy", {"RC_SHARD_FUSED": "0"}),
+                         ("sharded_nccl", {"RC_SHARD_TRANSPORT": "collective"})):
+            os.environ.update(env)
+            ts = radiocore.Tuner(cuda=True)
+            sharding.shard_tuner(ts, centers, B, make, F0, N, world, rank)
+            load = sharding.ShardedLoad(ts)
+            for k_ in env:
+                del os.environ[k_]
+            out[tag + "_mode"] = (load.transport, load.fused)
+            out["arc"] = (load.x_lo, load.x_len)
+            load.post(branches[0])
+            for b in range(BLOCKS):
+                if b + 1 < BLOCKS:
+                    load.post(branches[b + 1])
+                sub = load.take()
+                ts.load_subband(sub)
+                out[(tag, b)] = slice_of(ts, ts.run_all(numpy_output=True), range(len(mine))).copy()
+                if b == 0 and tag == "sharded":
+                    out["subband"] = sub[:load.x_len].cpu().numpy()
+            torch.cuda.synchronize()
+            dist.barrier()
+            del load, ts
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), out, allow_pickle=True)
         dist.barrier()

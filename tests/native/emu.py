@@ -303,3 +303,25 @@ def subband_combine(pieces, n_input, k0_base):
     out = np.empty_like(pieces)
     _check(lib().rc_subband_combine(0, g, C.c_int64(p), C.c_int64(n_input), C.c_int64(k0_base), _p(pieces), _p(out), None))
     return out
+
+
+class ScatterSeg(C.Structure):
+    _fields_ = [("k1", C.c_int32), ("reserved", C.c_int32), ("j_lo", C.c_int64), ("j_hi", C.c_int64), ("dst", C.c_void_p)]
+
+
+def fft_scatter(fft_plan, x, pieces):
+    """rc_fft_exec_scatter: output piece p of the transform lands in the complex64 array pieces[p]."""
+    x = _c64(x)
+    arr = (C.c_void_p * len(pieces))(*[p.ctypes.data for p in pieces])
+    _check(lib().rc_fft_exec_scatter(fft_plan._h, -1, _p(x), arr, len(pieces), C.c_int64(len(pieces[0])), None))
+
+
+def subband_combine_scatter(pieces, n_input, k0_base, segs):
+    """rc_subband_combine_scatter; segs: [(k1, j_lo, j_hi, destination array, first index)]."""
+    pieces = _c64(pieces)
+    g, p = pieces.shape
+    arr = (ScatterSeg * len(segs))()
+    for a, (k1, j0, j1, dst, pos) in zip(arr, segs):
+        a.k1, a.reserved, a.j_lo, a.j_hi, a.dst = k1, 0, j0, j1, dst.ctypes.data + 8 * pos
+    _check(lib().rc_subband_combine_scatter(0, g, C.c_int64(p), C.c_int64(n_input), C.c_int64(k0_base), _p(pieces),
+                                            arr, len(segs), None))

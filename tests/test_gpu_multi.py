@@ -56,6 +56,9 @@ def test_one_stream_channel_shards(tmp_path, world):
             assert np.array_equal(g[("bcast", b)], g[("full", b)]), f"bcast differs from one GPU, block {b}"
             want = np.concatenate([ref[c] for c in g["mine"]])
             worst = max(worst, parity.assert_parity(g[("sharded", b)], want, f"sharded b{b}"))
+            # the three transports move the same numbers
+            assert np.array_equal(g[("sharded_copy", b)], g[("sharded", b)]), f"copy transport differs, block {b}"
+            assert np.array_equal(g[("sharded_nccl", b)], g[("sharded", b)]), f"NCCL transport differs, block {b}"
             parity.assert_parity(g[("full", b)], want, f"full b{b}")
             if b == 0:
                 lo, length = g["arc"]
@@ -65,4 +68,5 @@ def test_one_stream_channel_shards(tmp_path, world):
                 err = np.abs(g["subband"] - sub)
                 assert np.sqrt(np.mean(err ** 2)) <= 2e-6 * np.sqrt(np.mean(np.abs(X) ** 2))
                 assert np.max(err) <= 2e-6 * np.max(np.abs(X)) + 5e-6 * np.sqrt(np.mean(np.abs(X) ** 2))
-    print(f"world {world}: sharded-load audio worst rel err {worst:.2e}")
+    print(f"world {world}: sharded-load audio worst rel err {worst:.2e}; modes",
+          got[0]["sharded_mode"], got[0]["sharded_copy_mode"], got[0]["sharded_nccl_mode"])

@@ -149,3 +149,43 @@ def test_sharded_load_replay(emu, world):
         for i, c in enumerate(mine):
             ref = o.channels()[c].demodulator.run(o.run(c))
             parity.assert_parity(audio[i], ref, f"world {world} rank {d} ch {c}")
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_load_fused_stores_replay(emu, world):
+    """The fused variants -- rc_fft_exec_scatter (last pass stores each piece into its combiner's
+    buffer) and rc_subband_combine_scatter (the combine stores every bin into the sub-bands that read
+    it) -- against the plain kernels + array-slicing exchanges: bit-identical sub-bands."""
+    from bench_support import synth
+    from radiocore.tools import sharding
+    N, B, C_ = 128_000, 16_000, 8
+    offs = synth.tiling_centers(N, C_, B)
+    x = synth.wideband(N, offs, B, seed=78)
+    arcs = []
+    for r in range(world):
+        t = emu.Tuner()
+        sharding.shard_tuner(t, [1e8 + f for f in offs], B, lambda c: None, 1e8, N, world, r)
+        arcs.append(sharding.covering_arc(t.needed_bins(), N))
+    plan = sharding.SubbandPlan(N, world, arcs)
+    fft = emu.Fft(plan.m)
+    # plain
+    F = [fft(x[g::world]) for g in range(world)]
+    Y = [emu.subband_combine(np.stack([F[g][p * plan.p:(p + 1) * plan.p] for g in range(world)]), N, p * plan.p)
+         for p in range(world)]
+    want = []
+    for d in range(world):
+        sub = np.zeros(arcs[d][1], dtype=np.complex64)
+        for src in range(world):
+            for k1, j0, j1, pos in plan.runs(src, d):
+                sub[pos: pos + (j1 - j0)] = Y[src][k1, j0:j1]
+        want.append(sub)
+    # fused: R[p] is rank p's [G][P] receive buffer, subs[d] rank d's sub-band
+    R = [np.zeros((world, plan.p), dtype=np.complex64) for _ in range(world)]
+    subs = [np.zeros(arcs[d][1], dtype=np.complex64) for d in range(world)]
+    for g in range(world):
+        emu.fft_scatter(fft, x[g::world], [R[p][g] for p in range(world)])
+    for p in range(world):
+        segs = [(k1, j0, j1, subs[d], pos) for d in range(world) for k1, j0, j1, pos in plan.runs(p, d)]
+        emu.subband_combine_scatter(R[p], N, p * plan.p, segs)
+    for d in range(world):
+        assert np.array_equal(subs[d], want[d]), d
