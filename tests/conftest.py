@@ -10,3 +10,15 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "radio-core_b20
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: long-running")
+
+
+def pytest_collection_modifyitems(config, items):
+    """A hung kernel must fail a test, not eat the GPU session: per-test timeout (pytest-timeout)."""
+    try:
+        import pytest
+        import pytest_timeout  # noqa: F401
+    except Exception:
+        return
+    for item in items:
+        if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(900))

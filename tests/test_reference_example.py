@@ -1,5 +1,9 @@
 """The reference's examples/multi_fm_server.py, UNMODIFIED, on top of this package.
 
+Runs in a CHILD process (`python tests/test_reference_example.py <out.npy>`): the script never closes
+its ZeroMQ socket, so the interpreter that ran it is left with a context that blocks at exit; the
+child saves what the subscriber received and leaves with os._exit.
+
 The script is the vendored byte-for-byte copy (oracle/_ref/examples, made by oracle/make_ref.py;
 /root/reference/examples in the build container).  It is executed as ``__main__`` with two
 stand-ins registered before it starts: a ``SoapySDR`` module whose device plays a synthetic
@@ -91,34 +95,19 @@ def _soapy_stub(block, rate_limit):
     return mod
 
 
-def test_multi_fm_server_unmodified():
-    zmq = pytest.importorskip("zmq")
+def _serve(out_path):
+    """Child process: run the unmodified script until the subscriber has two blocks per station."""
+    import zmq
     script = _script()
-    if script is None:
-        pytest.skip("no copy of the reference's examples (run oracle/make_ref.py in the build container)")
+    for p in (ROOT, os.path.join(ROOT, "radio-core_b200"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
     import radiocore
     assert "radio-core_b200" in radiocore.__file__            # the drop-in, not the reference package
-
-    # the script's own Config: 10 Msps, WBFM 96.9 MHz, MFM 94.5 MHz, FM 97.5 MHz, 240 kHz wide, 48 kHz audio
-    N, B, A = 10_000_000, 240_000, 48_000
-    freqs = (96.9e6, 94.5e6, 97.5e6)
-    kinds = ("WBFM", "MFM", "FM")
-    o = oracle.Tuner()
-    for f, k in zip(freqs, kinds):
-        o.add_channel(f, B, getattr(oracle, k)(B, A, 75e-6))
-    o.request_bandwidth(N)
-    f_in = o.input_frequency
-    block = synth.wideband(N, [f - f_in for f in freqs], B, seed=19, stereo=True, deviation=60e3)
-
-    want = []                                   # oracle audio of the first three blocks of the looped stream
-    for _ in range(3):
-        o.load(block)
-        want.append([ch.demodulator.run(o.run(ch.index)) for ch in o.channels()])
-
+    block, f_in, freqs = _stream()
     stub = _soapy_stub(block, rate_limit=40e6)
     sys.modules["SoapySDR"] = stub
     got = {f: [] for f in freqs}
-    stop = threading.Event()
 
     def subscriber():
         ctx = zmq.Context.instance()
@@ -126,8 +115,8 @@ def test_multi_fm_server_unmodified():
         sock.connect("tcp://127.0.0.1:5555")
         sock.setsockopt(zmq.SUBSCRIBE, b"")
         sock.setsockopt(zmq.RCVTIMEO, 200)
-        deadline = time.time() + 90
-        while not stop.is_set() and time.time() < deadline:
+        deadline = time.time() + 120
+        while time.time() < deadline:
             try:
                 topic, payload = sock.recv_multipart()
             except zmq.Again:
@@ -140,21 +129,58 @@ def test_multi_fm_server_unmodified():
         sock.close(0)
         _thread.interrupt_main()                # what Ctrl-C does to the script
 
-    th = threading.Thread(target=subscriber, daemon=True)
-    th.start()
-    argv = sys.argv
+    threading.Thread(target=subscriber, daemon=True).start()
+    sys.argv = [script]
+    code = 1
     try:
-        sys.argv = [script]
-        with pytest.raises(SystemExit):
-            runpy.run_path(script, run_name="__main__")
-    finally:
-        sys.argv = argv
-        stop.set()
-        sys.modules.pop("SoapySDR", None)
-    th.join(10)
+        runpy.run_path(script, run_name="__main__")
+    except SystemExit:                          # the script's own KeyboardInterrupt handler: stop threads, sys.exit
+        code = 0
+    np.save(out_path, {"got": got, "calls": stub.Device.calls}, allow_pickle=True)
+    sys.stdout.flush()
+    os._exit(code)                              # skip interpreter teardown: the script's PUB socket is still open
 
-    assert ("rate", float(N)) in stub.Device.calls and ("freq", f_in) in stub.Device.calls
-    for i, (f, k) in enumerate(zip(freqs, kinds)):
+
+N, B, A = 10_000_000, 240_000, 48_000           # the script's own Config: 10 Msps, three 240 kHz stations, 48 kHz audio
+FREQS = (96.9e6, 94.5e6, 97.5e6)
+KINDS = ("WBFM", "MFM", "FM")
+
+
+def _oracle_tuner():
+    o = oracle.Tuner()
+    for f, k in zip(FREQS, KINDS):
+        o.add_channel(f, B, getattr(oracle, k)(B, A, 75e-6))
+    o.request_bandwidth(N)
+    return o
+
+
+def _stream():
+    f_in = _oracle_tuner().input_frequency
+    block = synth.wideband(N, [f - f_in for f in FREQS], B, seed=19, stereo=True, deviation=60e3)
+    return block, f_in, FREQS
+
+
+def test_multi_fm_server_unmodified(tmp_path):
+    import subprocess
+    pytest.importorskip("zmq")
+    if _script() is None:
+        pytest.skip("no copy of the reference's examples (run oracle/make_ref.py in the build container)")
+    out = str(tmp_path / "served.npy")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "radio-core_b200"), os.path.join(ROOT, "oracle")]))
+    proc = subprocess.run([sys.executable, os.path.abspath(__file__), out], env=env, timeout=300,
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert proc.returncode == 0, proc.stdout.decode(errors="replace")[-3000:]
+    res = np.load(out, allow_pickle=True).item()
+    got, calls = res["got"], res["calls"]
+
+    block, f_in, _ = _stream()
+    o = _oracle_tuner()
+    want = []                                   # oracle audio of the first three blocks of the looped stream
+    for _ in range(3):
+        o.load(block)
+        want.append([ch.demodulator.run(o.run(ch.index)) for ch in o.channels()])
+    assert ("rate", float(N)) in calls and ("freq", f_in) in calls
+    for i, (f, k) in enumerate(zip(FREQS, KINDS)):
         assert len(got[f]) >= 2, f"no audio received for {f}"
         nch = 2 if k == "WBFM" else 1
         for payload in got[f][:2]:
@@ -164,3 +190,7 @@ def test_multi_fm_server_unmodified():
             errs = [parity.errors(a, np.asarray(w[i]).reshape(A, nch)) for w in want]
             rel_peak, margin = min(errs, key=lambda e: e[1])
             assert rel_peak <= parity.TOL and margin <= 1.0, (f, k, errs)
+
+
+if __name__ == "__main__":
+    _serve(sys.argv[1])
