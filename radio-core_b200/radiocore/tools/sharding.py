@@ -218,6 +218,8 @@ class ShardedLoad:
         tuner.set_subband(self.x_lo, self.x_len)
         self._k = kernels if kernels is not None else _NativeKernels(self.plan, self._rank)
         k, plan = self._k, self.plan
+        self._send = [plan.runs(self._rank, d) for d in range(self._world)]
+        self._recv = [plan.runs(p, self._rank) for p in range(self._world)]
         self._depth = max(2, depth)
         pad = 1 << 16                                               # the gather's tensor map describes whole rows past x_len
         slot_len = max(b for _, b in arcs) + pad
@@ -263,8 +265,6 @@ class ShardedLoad:
                 self._segs.append(k.make_segments(segs))
         self._turn = 0
         self._pending = collections.deque()
-        self._send = [plan.runs(self._rank, d) for d in range(self._world)]
-        self._recv = [plan.runs(p, self._rank) for p in range(self._world)]
         self.bytes_exchanged = 8 * (2 * plan.m - 2 * plan.p) if self._world > 1 else 0   # sent per block, both exchanges (halo aside)
 
     # ---- the two exchanges
