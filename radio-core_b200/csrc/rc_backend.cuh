@@ -37,7 +37,7 @@ inline cudaError_t dev_zero(void* d, size_t n, cudaStream_t) { memset(d, 0, n); 
 inline cudaError_t dev_sync(cudaStream_t) { return cudaSuccess; }
 
 template <class F> cudaError_t launch_ew(long long n, int batch, const F& f, cudaStream_t,
-                                         const char* = "ew", double = 0.0) {
+                                         const char* = "ew", double = 0.0, int = 0) {
     for (int b = 0; b < batch; b++)
         for (long long i = 0; i < n; i++) f(b, i);
     return cudaSuccess;
@@ -62,12 +62,14 @@ template <class F> __global__ void __launch_bounds__(256) ew_kernel(const F f, l
 
 // Elementwise launch: f(batch, i) for i in [0, n).  Grid is sized in whole
 // waves of the 148 SMs (8 resident 256-thread CTAs each) and grid-strided.
+// ctas_per_sm > 0 caps the grid at that many CTAs per SM (persistent grid-stride): for kernels bound
+// by something other than HBM (NVLink stores) that should leave SM slots to concurrent streams.
 template <class F> cudaError_t launch_ew(long long n, int batch, const F& f, cudaStream_t stream,
-                                         const char* tag = "ew", double bytes = 0.0) {
+                                         const char* tag = "ew", double bytes = 0.0, int ctas_per_sm = 0) {
     if (n <= 0 || batch <= 0) return cudaSuccess;
     ProfileScope scope(tag, bytes, stream);
     long long blocks = (n + 255) / 256;
-    long long cap = (148LL * 8 * 4 + batch - 1) / batch;
+    long long cap = ((ctas_per_sm > 0 ? 148LL * ctas_per_sm : 148LL * 8 * 4) + batch - 1) / batch;
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)batch);

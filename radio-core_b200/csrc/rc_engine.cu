@@ -1006,12 +1006,16 @@ int rc_subband_combine_scatter(int device, int n_ranks, int64_t piece_len, int64
     const double bytes = 16.0 * (double)piece_len * n_ranks;
     const float2* F = (const float2*)pieces_dev;
     const double m2n = -2.0 / (double)n_input;
+    // NVLink-bound: a few resident CTAs per SM keep the links busy and leave the rest of the SM to the
+    // channel kernels of the previous block running beside it (RC_SCATTER_CTAS: experiments)
+    int cps = 2;
+    if (const char* env = getenv("RC_SCATTER_CTAS")) cps = atoi(env);
     cudaError_t err;
     switch (n_ranks) {
-        case 2: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<2>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes); break;
-        case 4: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<4>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes); break;
-        case 8: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<8>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes); break;
-        case 16: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<16>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes); break;
+        case 2: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<2>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 4: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<4>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 8: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<8>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 16: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<16>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
         default: return fail(RC_ERR_UNSUPPORTED, "subband_combine_scatter: 2, 4, 8 or 16 ranks");
     }
     RC_API_CUDA(err, "subband combine scatter");

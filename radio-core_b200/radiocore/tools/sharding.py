@@ -251,9 +251,12 @@ class ShardedLoad:
         # writes every bin into the sub-band of the rank(s) that read it -- compute and NVLink transfer in
         # one kernel each, a barrier after each, no staging arrays and no copies.  RC_SHARD_FUSED=0 keeps
         # the kernels local and pushes with device-to-device copies instead.
-        self.fused = (self._peer is not None and hasattr(k, "fft_scatter") and plan.p % 2 == 0
-                      and os.environ.get("RC_SHARD_FUSED", "1") != "0")
-        if self.fused:
+        mode = os.environ.get("RC_SHARD_FUSED", "1")
+        ok = self._peer is not None and hasattr(k, "fft_scatter") and plan.p % 2 == 0
+        self.fused_fft = ok and mode in ("1", "fft")            # exchange 1 = stores of the FFT's last pass
+        self.fused_combine = ok and mode in ("1", "combine")     # exchange 2 = stores of the combine
+        self.fused = self.fused_fft and self.fused_combine
+        if ok:
             g, p8 = self._rank, 8 * plan.p
             self._piece_bases = [self._peer.ptrs[d] + self._peer.r_offset_bytes + g * p8 for d in range(self._world)]
             self._segs = []
@@ -337,21 +340,23 @@ class ShardedLoad:
         self._turn = (self._turn + 1) % self._depth
         done = self._k.begin(x_branch, slot, ready)
         self._mark("begin")
-        if self.fused:
-            idx = next(i for i, t in enumerate(self._slots) if t is slot)
+        if self.fused_fft:
             self._k.fft_scatter(x_branch, self._piece_bases)
             self._mark("local_fft+scatter")
             self._peer.barrier(0)
             self._mark("barrier_pieces")
-            self._k.combine_scatter(self._R, self._rank * self.plan.p, self._segs[idx])
-            self._mark("combine+scatter")
-            self._peer.barrier(1)
-            self._mark("barrier_bins")
         else:
             self._k.fft(x_branch, self._F)
             self._mark("local_fft")
             self._exchange_pieces()
             self._mark("exchange_pieces")
+        if self.fused_combine:
+            idx = next(i for i, t in enumerate(self._slots) if t is slot)
+            self._k.combine_scatter(self._R, self._rank * self.plan.p, self._segs[idx])
+            self._mark("combine+scatter")
+            self._peer.barrier(1)
+            self._mark("barrier_bins")
+        else:
             self._k.combine(self._R, self._Y, self._rank * self.plan.p)
             self._mark("combine")
             self._exchange_bins(slot)
