@@ -7,7 +7,7 @@ set -x
 mkdir -p gpurun_out
 python __graft_entry__.py > gpurun_out/build.log 2>&1
 nvidia-smi topo -m > gpurun_out/topo_${G}gpu.txt 2>&1
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -s > gpurun_out/pytest_multi_${G}gpu.log 2>&1; tail -8 gpurun_out/pytest_multi_${G}gpu.log
+timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -s -k "$G" > gpurun_out/pytest_multi_${G}gpu.log 2>&1; tail -8 gpurun_out/pytest_multi_${G}gpu.log
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 \
   bench.py --gpus $G --steps 20 --warmup 5 > gpurun_out/bench_${G}gpu.json 2> gpurun_out/bench_${G}gpu.err
 tail -3 gpurun_out/bench_${G}gpu.err
