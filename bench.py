@@ -45,6 +45,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "complex Msamples/s through multi-WBFM chain at 1/2/4/8 GPU; HBM GB/s vs peak"
 UNIT = "Msamples/s"
+NVLINK_PEAK_GBS = 770.0          # measured peer copy, per direction per GPU (B200_PROFILING.md)
 
 WORKLOADS = {
     # name: (N, C, B, A, demod, description)
@@ -495,7 +496,7 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
         tuner.run_all()
     ev1.record()
     torch.cuda.synchronize()
-    res["decomposition"] = {"transport": load.transport, "load_pipeline_ms": {k: round(v, 4) for k, v in phases.items()},
+    res["decomposition"] = {"transport": load.transport, "fused": bool(getattr(load, "fused", False)), "load_pipeline_ms": {k: round(v, 4) for k, v in phases.items()},
                             "load_pipeline_total_ms": round(sum(phases.values()), 4),
                             "channel_stage_ms": round(ev0.elapsed_time(ev1) / 3, 4),
                             "note": "each measured alone on rank 0; in the timed step block k+1's load pipeline overlaps block k's channel stage"}
@@ -635,12 +636,28 @@ def run_b200(args, rank, world, local_rank):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(args.workload if world == 1 else "", {}).get(top)
     except Exception:
         pass
+    # kernels whose stores ARE an NVLink exchange (sharded load, fused transport): bound by the link, not HBM
+    nvl = res.get("nvlink_bytes_sent_per_rank_per_step")
+    fused_tags = []
+    if nvl and res.get("decomposition", {}).get("fused"):
+        last_fft = [t for t in table if t.startswith("tuner.local_fft/")]
+        fused_tags = [t for t in (last_fft[-1:] + ["tuner.subband_combine_scatter"]) if t in table]
+        for t in fused_tags:
+            g = (nvl / 2) / (table[t]["avg_ms"] * 1e-3) / 1e9
+            table[t]["nvlink_bytes_per_launch"] = nvl / 2
+            table[t]["nvlink_GBps"] = round(g, 1)
+            table[t]["frac_of_nvlink_peak"] = round(g / NVLINK_PEAK_GBS, 4)
     roofline = None
     if top:
         kt = table[top]
         roofline = {"kernel": top, "bound": "hbm", "achieved": kt["GBps"], "peak": peak_gbs, "unit": "GB/s",
                     "frac": round(kt["GBps"] / peak_gbs, 4), "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": kt["avg_ms"], "share_of_step": round(kt["ms_per_step"] / ms_per_step, 4)}
+        if top in fused_tags:
+            roofline.update({"bound": "nvlink", "achieved": kt["nvlink_GBps"], "peak": NVLINK_PEAK_GBS,
+                             "frac": kt["frac_of_nvlink_peak"], "traffic": None,
+                             "peak_source": "measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md: 770 GB/s)",
+                             "note": "fused compute + exchange kernel: its remote stores cross NVLink; HBM side: %.1f GB/s" % kt["GBps"]})
     multi = {"single": "n/a", "independent": "independent sub-band stream per GPU, no data-path collective",
              "sharded": "one stream: channel slices + sharded Tuner.load (commutator branches, local N/G-point FFT, "
                         "two NVLink all-to-all exchanges, radix-G combine), no reduction",
