@@ -421,11 +421,12 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
     branch = x_dev[ctx.rank::ctx.world].contiguous()
 
     def step():
-        load.post(branch)                           # block k+1: local FFT + exchanges on the side stream ...
+        load.post(branch)                           # block k+lanes: local FFT + exchanges on a side stream ...
         tuner.load_subband(load.take())             # ... while block k is demodulated
         tuner.run_all()
 
-    load.post(branch)                               # prime: one block ahead
+    for _ in range(load.lanes):                     # prime: one block ahead per pipeline lane
+        load.post(branch)
     ms_total, launches, kernels, clocks = time_steps(ctx, step, steps, warmup, profile)
     res = {"ms_per_step": ms_total / steps, "launches": launches, "kernels": kernels, "clocks": clocks,
            "channels": len(mine), "nvlink_bytes_sent_per_rank_per_step": load.bytes_exchanged}
@@ -438,7 +439,8 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
         host = [torch.empty(m, dtype=torch.complex64).pin_memory() for _ in range(2)]
         for h in host:
             h.copy_(branch)
-        stage = [torch.empty(m, dtype=torch.complex64, device=ctx.device) for _ in range(3)]
+        nstage = load.lanes + 2
+        stage = [torch.empty(m, dtype=torch.complex64, device=ctx.device) for _ in range(nstage)]
         d2h = 4 * sum(size * nchn for _, size, nchn in tuner.audio_slices())
         state = {"i": 0}
 
@@ -447,9 +449,9 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
             state["i"] += 1
             ev = torch.cuda.Event()
             with torch.cuda.stream(copy_stream):
-                stage[i % 3].copy_(host[i % 2], non_blocking=True)
+                stage[i % nstage].copy_(host[i % 2], non_blocking=True)
                 ev.record(copy_stream)
-            load.post(stage[i % 3], ready=ev)
+            load.post(stage[i % nstage], ready=ev)
 
         def run(k):
             checksum = 0.0
@@ -462,7 +464,8 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
         while load.in_flight():
             load.take()
         torch.cuda.synchronize()
-        send_next()
+        for _ in range(load.lanes):
+            send_next()
         run(3)
         ctx.barrier()
         t0 = time.perf_counter()
@@ -496,7 +499,7 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
         tuner.run_all()
     ev1.record()
     torch.cuda.synchronize()
-    res["decomposition"] = {"transport": load.transport, "fused": bool(getattr(load, "fused", False)), "load_pipeline_ms": {k: round(v, 4) for k, v in phases.items()},
+    res["decomposition"] = {"transport": load.transport, "lanes": load.lanes, "fused": bool(getattr(load, "fused", False)), "load_pipeline_ms": {k: round(v, 4) for k, v in phases.items()},
                             "load_pipeline_total_ms": round(sum(phases.values()), 4),
                             "channel_stage_ms": round(ev0.elapsed_time(ev1) / 3, 4),
                             "note": "each measured alone on rank 0; in the timed step block k+1's load pipeline overlaps block k's channel stage"}

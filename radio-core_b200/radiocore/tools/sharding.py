@@ -202,7 +202,7 @@ class ShardedLoad:
     a NumPy stand-in to check the plan and the exchanges).
     """
 
-    def __init__(self, tuner, depth: int = 2, kernels=None, group=None):
+    def __init__(self, tuner, depth: int = 0, kernels=None, group=None, lanes: int = 0):
         self._world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._group = group
@@ -216,15 +216,23 @@ class ShardedLoad:
         self.plan = SubbandPlan(n, self._world, arcs)
         self.x_lo, self.x_len = arcs[self._rank]
         tuner.set_subband(self.x_lo, self.x_len)
-        self._k = kernels if kernels is not None else _NativeKernels(self.plan, self._rank)
-        k, plan = self._k, self.plan
+        # Pipeline lanes: consecutive blocks alternate between `lanes` independent side streams (own FFT
+        # plan, own piece buffer R, own barrier channels), so the HBM-bound local FFT of block k+2 runs
+        # beside the NVLink-bound exchange of block k+1.  `lanes` blocks can be posted ahead of take().
+        if lanes <= 0:
+            lanes = int(os.environ.get("RC_SHARD_LANES", "2")) if kernels is None else 1
+        self.lanes = max(1, lanes)
+        plan = self.plan
+        self._ks = [kernels] if kernels is not None else [_NativeKernels(plan, self._rank) for _ in range(self.lanes)]
+        self.lanes = len(self._ks)
+        self._k = k = self._ks[0]
         self._send = [plan.runs(self._rank, d) for d in range(self._world)]
         self._recv = [plan.runs(p, self._rank) for p in range(self._world)]
-        self._depth = max(2, depth)
+        self._depth = max(self.lanes + 1, depth)
         pad = 1 << 16                                               # the gather's tensor map describes whole rows past x_len
         slot_len = max(b for _, b in arcs) + pad
-        self._F = k.empty(plan.m)                                   # F_g, natural order: piece p = [p*P, (p+1)*P)
-        self._Y = k.empty(plan.m)                                   # [G][P]: bins k1*M + rank*P + j
+        self._Fs = [k.empty(plan.m) for _ in range(self.lanes)]     # F_g, natural order: piece p = [p*P, (p+1)*P)
+        self._Ys = [k.empty(plan.m) for _ in range(self.lanes)]     # [G][P]: bins k1*M + rank*P + j
         # Transport of the two exchanges.  "peer": the receive buffers (R and the sub-band slots) live in
         # symmetric memory mapped into every rank (torch.distributed._symmetric_memory); a rank PUSHES its
         # pieces / runs straight into the peers' buffers with device-to-device copies over NVLink and a
@@ -235,15 +243,15 @@ class ShardedLoad:
         want = os.environ.get("RC_SHARD_TRANSPORT", "peer" if kernels is None else "collective")
         if want == "peer" and self._world > 1:
             try:
-                self._peer = _PeerBuffers(plan.m, slot_len, self._depth, self._world, self._rank, group)
+                self._peer = _PeerBuffers(plan.m, slot_len, self._depth, self._world, self._rank, group, self.lanes)
             except Exception as exc:                                # pragma: no cover - depends on the box
                 import warnings
                 warnings.warn(f"radiocore: symmetric-memory transport unavailable ({exc!r}); using NCCL send/recv")
         self.transport = "peer" if self._peer is not None else "collective"
         if self._peer is not None:
-            self._R, self._slots = self._peer.R, self._peer.slots
+            self._Rs, self._slots = self._peer.R, self._peer.slots
         else:
-            self._R = k.empty(plan.m)                               # [G][P]: piece `rank` of every F_g
+            self._Rs = [k.empty(plan.m) for _ in range(self.lanes)]  # [G][P]: piece `rank` of every F_g
             self._slots = [k.empty(slot_len) for _ in range(self._depth)]
         self.phase_events = None                                    # set to [] to record (name, event) pairs per post()
         # With peer-mapped buffers the two exchanges can be the STORES of the kernels themselves: the
@@ -258,7 +266,8 @@ class ShardedLoad:
         self.fused = self.fused_fft and self.fused_combine
         if ok:
             g, p8 = self._rank, 8 * plan.p
-            self._piece_bases = [self._peer.ptrs[d] + self._peer.r_offset_bytes + g * p8 for d in range(self._world)]
+            self._piece_bases = [[self._peer.ptrs[d] + self._peer.r_offset_bytes(ln) + g * p8 for d in range(self._world)]
+                                 for ln in range(self.lanes)]
             self._segs = []
             for idx in range(self._depth):
                 segs = []
@@ -267,23 +276,26 @@ class ShardedLoad:
                     segs += [(k1, j0, j1, base + 8 * pos) for k1, j0, j1, pos in self._send[d]]
                 self._segs.append(k.make_segments(segs))
         self._turn = 0
+        self._block = 0
+        self._last_fft_done = None
         self._pending = collections.deque()
         self.bytes_exchanged = 8 * (2 * plan.m - 2 * plan.p) if self._world > 1 else 0   # sent per block, both exchanges (halo aside)
 
     # ---- the two exchanges
-    def _exchange_pieces(self):
+    def _exchange_pieces(self, lane):
         """R[g] = F_g[rank*P : (rank+1)*P] from every rank g (equal-split all-to-all)."""
+        F, R = self._Fs[lane], self._Rs[lane]
         if self._world == 1:
-            self._R.copy_(self._F)
+            R.copy_(F)
             return
         if self._peer is not None:
             p, g = self.plan.p, self._rank
             for step in range(self._world):                          # start with the neighbour: spread the traffic
                 d = (g + step) % self._world
-                self._peer.R_of(d)[g * p:(g + 1) * p].copy_(self._F[d * p:(d + 1) * p], non_blocking=True)
-            self._peer.barrier(0)
+                self._peer.R_of(d, lane)[g * p:(g + 1) * p].copy_(F[d * p:(d + 1) * p], non_blocking=True)
+            self._peer.barrier(2 * lane)
             return
-        out, inp = _as_real(self._R), _as_real(self._F)
+        out, inp = _as_real(R), _as_real(F)
         if dist.get_backend(self._group) == "nccl":
             dist.all_to_all_single(out, inp, group=self._group)
             return
@@ -297,7 +309,7 @@ class ShardedLoad:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
-    def _exchange_bins(self, slot):
+    def _exchange_bins(self, slot, lane):
         """Exchange 2: the runs of SubbandPlan straight from Y into the destination sub-bands."""
         p = self.plan.p
         if self._peer is not None:
@@ -306,10 +318,10 @@ class ShardedLoad:
                 d = (self._rank + step) % self._world
                 dst = self._peer.slot_of(d, idx)
                 for k1, j0, j1, pos in self._send[d]:
-                    dst[pos: pos + (j1 - j0)].copy_(self._Y[k1 * p + j0: k1 * p + j1], non_blocking=True)
-            self._peer.barrier(1)
+                    dst[pos: pos + (j1 - j0)].copy_(self._Ys[lane][k1 * p + j0: k1 * p + j1], non_blocking=True)
+            self._peer.barrier(2 * lane + 1)
             return
-        Y, X = _as_real(self._Y), _as_real(slot)
+        Y, X = _as_real(self._Ys[lane]), _as_real(slot)
         ops = []
         for d in range(self._world):
             for k1, j0, j1, pos in self._send[d]:
@@ -338,30 +350,35 @@ class ShardedLoad:
             raise ValueError("the branch holds N / world_size samples")
         slot = self._slots[self._turn]
         self._turn = (self._turn + 1) % self._depth
-        done = self._k.begin(x_branch, slot, ready)
+        lane = self._block % self.lanes
+        self._block += 1
+        k = self._k = self._ks[lane]
+        done = k.begin(x_branch, slot, ready)
         self._mark("begin")
         if self.fused_fft:
-            self._k.fft_scatter(x_branch, self._piece_bases)
+            k.fft_scatter(x_branch, self._piece_bases[lane])
             self._mark("local_fft+scatter")
-            self._peer.barrier(0)
+            self._last_fft_done = getattr(k, "_fft_done", None)
+            self._peer.barrier(2 * lane)
             self._mark("barrier_pieces")
         else:
-            self._k.fft(x_branch, self._F)
+            k.fft(x_branch, self._Fs[lane])
             self._mark("local_fft")
-            self._exchange_pieces()
+            self._last_fft_done = getattr(k, "_fft_done", None)
+            self._exchange_pieces(lane)
             self._mark("exchange_pieces")
         if self.fused_combine:
             idx = next(i for i, t in enumerate(self._slots) if t is slot)
-            self._k.combine_scatter(self._R, self._rank * self.plan.p, self._segs[idx])
+            k.combine_scatter(self._Rs[lane], self._rank * self.plan.p, self._segs[idx])
             self._mark("combine+scatter")
-            self._peer.barrier(1)
+            self._peer.barrier(2 * lane + 1)
             self._mark("barrier_bins")
         else:
-            self._k.combine(self._R, self._Y, self._rank * self.plan.p)
+            k.combine(self._Rs[lane], self._Ys[lane], self._rank * self.plan.p)
             self._mark("combine")
-            self._exchange_bins(slot)
+            self._exchange_bins(slot, lane)
             self._mark("exchange_bins")
-        self._pending.append((slot, self._k.end(done)))
+        self._pending.append((slot, k.end(done), k))
 
     def _mark(self, name):
         if self.phase_events is not None and hasattr(self._k, "mark"):
@@ -381,8 +398,8 @@ class ShardedLoad:
         """Sub-band of the oldest posted block (bins [x_lo, x_lo + x_len)), ordered after its arrival."""
         if not self._pending:
             raise RuntimeError("take() without a posted block")
-        slot, ev = self._pending.popleft()
-        self._k.wait(ev, slot)
+        slot, ev, k = self._pending.popleft()
+        k.wait(ev, slot, self._last_fft_done)
         return slot
 
     def in_flight(self) -> int:
@@ -475,14 +492,14 @@ class _NativeKernels:
         self._ctx = None
         return ev
 
-    def wait(self, ev, slot):
+    def wait(self, ev, slot, newest_fft_done=None):
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
         # Take turns on the SMs: the caller's channel kernels for this block start once the local FFT
-        # of the block posted after it has finished, so they run beside that block's NVLink copies
-        # (copy engines, no SMs) instead of sharing HBM bandwidth with its FFT passes.
-        if self._fft_done is not None:
-            cur.wait_event(self._fft_done)
+        # of the block posted last has finished, so they run beside that block's NVLink-bound exchange
+        # instead of sharing HBM bandwidth with its FFT passes.
+        if newest_fft_done is not None:
+            cur.wait_event(newest_fft_done)
 
 
 class _PeerBuffers:
@@ -490,33 +507,35 @@ class _PeerBuffers:
     pieces) and the sub-band slots, mapped into every rank of the group, plus the stream-ordered
     barrier of the mapping (signal pads in the same symmetric allocation)."""
 
-    def __init__(self, m, slot_len, depth, world, rank, group):
+    def __init__(self, m, slot_len, depth, world, rank, group, lanes=1):
         import torch.distributed._symmetric_memory as symm
-        self._m, self._slot_len, self._depth = int(m), int(slot_len), int(depth)
-        total = 2 * (self._m + self._depth * self._slot_len)          # float32 words (complex64 = 2)
+        self._m, self._slot_len, self._depth, self._lanes = int(m), int(slot_len), int(depth), int(lanes)
+        total = 2 * (self._lanes * self._m + self._depth * self._slot_len)   # float32 words (complex64 = 2)
         self._buf = symm.empty(total, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
         self._hdl = symm.rendezvous(self._buf, group if group is not None else dist.group.WORLD)
         self._views = [self._buf if r == rank else self._hdl.get_buffer(r, (total,), torch.float32) for r in range(world)]
-        self.R = self._complex(self._buf, 0, self._m)
-        self.slots = [self._complex(self._buf, self._m + i * self._slot_len, self._slot_len) for i in range(depth)]
+        self.R = [self._complex(self._buf, ln * self._m, self._m) for ln in range(self._lanes)]
+        self.slots = [self._complex(self._buf, self._slot_first(i), self._slot_len) for i in range(depth)]
         self.ptrs = list(self._hdl.buffer_ptrs)                       # peer base addresses (for kernels that store remotely)
 
     @staticmethod
     def _complex(buf, first, count):
         return torch.view_as_complex(buf[2 * first: 2 * (first + count)].view(count, 2))
 
-    @property
-    def r_offset_bytes(self):
-        return 0
+    def _slot_first(self, i):
+        return self._lanes * self._m + i * self._slot_len
+
+    def r_offset_bytes(self, lane):
+        return 8 * lane * self._m
 
     def slot_offset_bytes(self, i):
-        return 8 * (self._m + i * self._slot_len)
+        return 8 * self._slot_first(i)
 
-    def R_of(self, r):
-        return self._complex(self._views[r], 0, self._m)
+    def R_of(self, r, lane):
+        return self._complex(self._views[r], lane * self._m, self._m)
 
     def slot_of(self, r, i):
-        return self._complex(self._views[r], self._m + i * self._slot_len, self._slot_len)
+        return self._complex(self._views[r], self._slot_first(i), self._slot_len)
 
     def barrier(self, channel):
         self._hdl.barrier(channel=channel)

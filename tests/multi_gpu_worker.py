@@ -72,10 +72,12 @@ def run(rank, world, port, out_dir, kind="MFM"):
                 del os.environ[k_]
             out[tag + "_mode"] = (load.transport, load.fused)
             out["arc"] = (load.x_lo, load.x_len)
-            load.post(branches[0])
+            ahead = load.lanes                                      # blocks posted ahead: one per pipeline lane
+            for b in range(min(ahead, BLOCKS)):
+                load.post(branches[b])
             for b in range(BLOCKS):
-                if b + 1 < BLOCKS:
-                    load.post(branches[b + 1])
+                if b + ahead < BLOCKS:
+                    load.post(branches[b + ahead])
                 sub = load.take()
                 ts.load_subband(sub)
                 out[(tag, b)] = slice_of(ts, ts.run_all(numpy_output=True), range(len(mine))).copy()

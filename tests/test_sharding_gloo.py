@@ -111,7 +111,7 @@ class _NumpyKernels:
     def end(self, token):
         return None
 
-    def wait(self, ev, slot):
+    def wait(self, ev, slot, newest_fft_done=None):
         pass
 
     def fft(self, x, out):
