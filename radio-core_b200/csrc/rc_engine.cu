@@ -583,7 +583,7 @@ int rc_engine_run(rc_engine* e, float* audio_dev, void* stream) {
         const long long B = bk.demod.B;
         const int batch = bk.demod.batch;
         RC_API_CUDA((fft_exec<+1>(*bk.planB, batch, tuner_gather(e, bk.d_roll, B), StoreAngle{bk.ang, B},
-                                  bk.w0, bk.w1, st, "tuner.channel_ifft", 12.0 * B * batch, 4.0 * B * batch)),
+                                  bk.w0, bk.w1, st, "tuner.channel_ifft", 8.0 * B * batch, 4.0 * B * batch)),   // DRAM bytes: the Hann table stays in L2
                     "tuner channel ifft");
         int rc = bk.demod.run_angle(bk.ang, audio_dev + bk.audio_offset, st);
         if (rc) return rc;

@@ -220,7 +220,7 @@ class ShardedLoad:
         # plan, own piece buffer R, own barrier channels), so the HBM-bound local FFT of block k+2 runs
         # beside the NVLink-bound exchange of block k+1.  `lanes` blocks can be posted ahead of take().
         if lanes <= 0:
-            lanes = int(os.environ.get("RC_SHARD_LANES", "2")) if kernels is None else 1
+            lanes = int(os.environ.get("RC_SHARD_LANES", "1")) if kernels is None else 1   # measured: 2 lanes gain nothing
         self.lanes = max(1, lanes)
         plan = self.plan
         self._ks = [kernels] if kernels is not None else [_NativeKernels(plan, self._rank) for _ in range(self.lanes)]
