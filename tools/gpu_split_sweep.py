@@ -28,6 +28,27 @@ if len(sys.argv) > 1 and sys.argv[1] == "all":
     })
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    # the transforms of configs 2 / 4 and of the short-block mode, at their batch sizes
+    CASES = {
+        (250_000, 32): ["500x500", "50x50x100", "100x50x50", "50x100x50", "400x625", "625x400", "250x1000", "40x125x50", "125x40x50", "125x50x40"],
+        (250_000, 64): ["500x500", "50x50x100", "100x50x50", "400x625", "125x40x50"],
+        (125_000, 32): ["250x500", "500x250", "200x625", "625x200", "50x50x50", "125x1000"],
+        (125_000, 64): ["250x500", "500x250", "200x625", "50x50x50"],
+        (125_000, 192): ["250x500", "500x250", "200x625", "50x50x50"],
+        (24_000, 32): ["160x150", "150x160", "300x80", "80x300", "600x40", "40x600"],
+        (24_000, 128): ["160x150", "150x160", "300x80", "80x300", "600x40"],
+        (24_000, 256): ["160x150", "150x160", "300x80", "80x300"],
+        (10_000_000, 1): ["200x100x500", "200x250x200", "250x200x200", "160x250x250", "125x400x200", "400x250x100", "320x125x250", "500x200x100", "100x100x1000"],
+        (16_000_000, 1): ["200x100x800", "200x200x400", "256x250x250", "250x256x250", "320x500x100", "160x400x250", "400x400x100", "640x250x100", "500x320x100"],
+        (8_000_000, 1): ["200x200x200", "160x250x200", "320x250x100", "500x160x100", "128x250x250", "250x256x125", "400x200x100", "250x160x200"],
+        (31_250, 256): ["125x250", "250x125", "50x625", "625x50"],
+        (15_625, 256): ["125x125"],
+        (32_000_000, 1): ["160x800x250", "320x400x250", "400x320x250", "200x400x400", "250x320x400", "500x256x250", "320x250x400"],
+        (128_000_000, 1): ["200x800x800", "800x640x250", "640x800x250", "500x512x500", "400x640x500", "640x400x500", "800x400x400"],
+    }
+
+
 def run(n, batch, split, reps=5):
     os.environ["RC_FFT_SPLIT"] = f"{n}:{split}"
     x = torch.randn(batch * n, 2, device="cuda")                 # interleaved complex64
