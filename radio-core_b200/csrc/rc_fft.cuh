@@ -769,6 +769,14 @@ inline bool fft_tuned_split(long long n, std::vector<int>& Rs) {
         {1000000LL, {200, 50, 100, 0}},
         {500000LL, {200, 50, 50, 0}},
         {250000LL, {500, 500, 0, 0}},
+        // round 2 sweep (profiles/r02_s12_split_sweep_small.txt): configs 2 / 4, short blocks, sharded load
+        {10000000LL, {160, 250, 250, 0}},
+        {16000000LL, {256, 250, 250, 0}},
+        {8000000LL, {320, 250, 100, 0}},
+        {31250LL, {250, 125, 0, 0}},
+        {125000LL, {250, 500, 0, 0}},
+        {128000000LL, {200, 800, 800, 0}},
+        {32000000LL, {160, 800, 250, 0}},
     };
     for (const Row& row : rows)
         if (row.n == n) {
