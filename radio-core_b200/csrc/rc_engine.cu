@@ -966,8 +966,10 @@ int rc_profile_report(char* buf, int capacity) {
 // ------------------------------------------------------- sharded-load pieces
 int rc_subband_combine(int device, int n_ranks, int64_t piece_len, int64_t n_input, int64_t k0_base,
                        const void* pieces_dev, void* bins_dev, void* stream) {
-    if (!pieces_dev || !bins_dev || piece_len < 1 || n_input < 1 || k0_base < 0)
+    if (!pieces_dev || !bins_dev || piece_len < 2 || n_input < 1 || k0_base < 0)
         return fail(RC_ERR_INVALID, "subband_combine: bad argument");
+    if ((piece_len & 1) || (((size_t)pieces_dev | (size_t)bins_dev) & 15))
+        return fail(RC_ERR_UNSUPPORTED, "subband_combine: even piece length and 16-byte aligned buffers");
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     const double bytes = 16.0 * (double)piece_len * n_ranks;
@@ -976,10 +978,10 @@ int rc_subband_combine(int device, int n_ranks, int64_t piece_len, int64_t n_inp
     const double m2n = -2.0 / (double)n_input;
     cudaError_t err;
     switch (n_ranks) {
-        case 2: err = launch_ew(piece_len, 1, SubbandCombineEw<2>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
-        case 4: err = launch_ew(piece_len, 1, SubbandCombineEw<4>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
-        case 8: err = launch_ew(piece_len, 1, SubbandCombineEw<8>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
-        case 16: err = launch_ew(piece_len, 1, SubbandCombineEw<16>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 2: err = launch_ew(piece_len / 2, 1, SubbandCombineEw<2>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 4: err = launch_ew(piece_len / 2, 1, SubbandCombineEw<4>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 8: err = launch_ew(piece_len / 2, 1, SubbandCombineEw<8>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 16: err = launch_ew(piece_len / 2, 1, SubbandCombineEw<16>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
         default: return fail(RC_ERR_UNSUPPORTED, "subband_combine: 2, 4, 8 or 16 ranks");
     }
     RC_API_CUDA(err, "subband combine");
@@ -988,8 +990,10 @@ int rc_subband_combine(int device, int n_ranks, int64_t piece_len, int64_t n_inp
 
 int rc_subband_combine_scatter(int device, int n_ranks, int64_t piece_len, int64_t n_input, int64_t k0_base,
                                const void* pieces_dev, const rc_scatter_seg* segs, int n_segs, void* stream) {
-    if (!pieces_dev || !segs || n_segs < 1 || piece_len < 1 || n_input < 1 || k0_base < 0)
+    if (!pieces_dev || !segs || n_segs < 1 || piece_len < 2 || n_input < 1 || k0_base < 0)
         return fail(RC_ERR_INVALID, "subband_combine_scatter: bad argument");
+    if ((piece_len & 1) || (((size_t)pieces_dev) & 15))
+        return fail(RC_ERR_UNSUPPORTED, "subband_combine_scatter: even piece length and 16-byte aligned pieces");
     ScatterTable tab;
     memset(&tab, 0, sizeof(tab));
     for (int i = 0; i < n_segs; i++) {
@@ -1012,10 +1016,10 @@ int rc_subband_combine_scatter(int device, int n_ranks, int64_t piece_len, int64
     if (const char* env = getenv("RC_SCATTER_CTAS")) cps = atoi(env);
     cudaError_t err;
     switch (n_ranks) {
-        case 2: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<2>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
-        case 4: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<4>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
-        case 8: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<8>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
-        case 16: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<16>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 2: err = launch_ew(piece_len / 2, 1, SubbandCombineScatterEw<2>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 4: err = launch_ew(piece_len / 2, 1, SubbandCombineScatterEw<4>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 8: err = launch_ew(piece_len / 2, 1, SubbandCombineScatterEw<8>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 16: err = launch_ew(piece_len / 2, 1, SubbandCombineScatterEw<16>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
         default: return fail(RC_ERR_UNSUPPORTED, "subband_combine_scatter: 2, 4, 8 or 16 ranks");
     }
     RC_API_CUDA(err, "subband combine scatter");
