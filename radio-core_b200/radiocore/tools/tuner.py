@@ -89,12 +89,14 @@ class Tuner:
         self._replan()
 
     def reset(self):
-        """Forget all channels (the reference's reset raises on the empty plan,
-        tuner.py:121-124,164; here it simply returns to the initial state)."""
+        """Forget all channels.  As in the reference (tuner.py:121-124,164) the re-plan of the now
+        empty channel list then raises ``ValueError`` (``min()`` of an empty sequence) -- the
+        channels are gone when it does, and ``add_channel`` can be called again."""
         self._bounds = []
         self._input_frequency = 0.0
         self._input_bandwidth = 0.0
         self._drop_engine()
+        self._replan()
 
     def _replan(self):
         edges_lo = [c.lower_frequency for c in self._bounds]
