@@ -421,7 +421,12 @@ class _NativeKernels:
         self._native, self._C = _native, C
         self._plan = plan
         self._dev = _device.device_index()
-        self._stream = torch.cuda.Stream()
+        # High priority: the block scheduler then dispatches this pipeline's CTAs -- notably the small
+        # resident grid of the NVLink-bound combine -- as soon as slots free up, instead of after the
+        # whole grid of whichever channel kernel of the caller's stream is in flight, so the link-bound
+        # kernel really runs BESIDE the HBM-bound channel kernels (RC_SHARD_PRIORITY=0: default priority).
+        prio = -1 if os.environ.get("RC_SHARD_PRIORITY", "1") != "0" else 0
+        self._stream = torch.cuda.Stream(priority=prio)
         self._fft = C.c_void_p()
         _native.check(_native.lib().rc_fft_create(self._dev, plan.m, 1, C.byref(self._fft)))
         self._ctx = None
@@ -498,7 +503,7 @@ class _NativeKernels:
         # Take turns on the SMs: the caller's channel kernels for this block start once the local FFT
         # of the block posted last has finished, so they run beside that block's NVLink-bound exchange
         # instead of sharing HBM bandwidth with its FFT passes.
-        if newest_fft_done is not None:
+        if newest_fft_done is not None and os.environ.get("RC_SHARD_TURNS", "1") != "0":
             cur.wait_event(newest_fft_done)
 
 
