@@ -260,6 +260,21 @@ class Tuner:
         return self._audio_host.numpy()
 
     # ------------------------------------------------- one block as one CUDA graph
+    def _graph_state(self):
+        self._ensure_engine()
+        g = self._graph
+        if g is None or g["engine"] is not self._engine:
+            n = int(self._input_bandwidth)
+            g = self._graph = {"engine": self._engine, "x": torch.empty(n, dtype=torch.complex64, device="cuda"),
+                               "graph": None, "warm": 0}
+        return g
+
+    def graph_input(self):
+        """The persistent device buffer the captured graph of ``step`` reads: a producer (the
+        host-to-device copy of the ingest side, another kernel) that writes the block straight into
+        it and then calls ``step(tuner.graph_input())`` saves the extra device copy."""
+        return self._graph_state()["x"]
+
     def step(self, input_signal, numpy_output: bool = False):
         """``load`` + ``run_all`` of one block replayed as ONE CUDA graph.
 
@@ -269,18 +284,15 @@ class Tuner:
         graph launch replaces the ~10-25 kernel launches of the block -- what matters for
         short blocks, whose kernels run for microseconds.  Same arithmetic and
         the same carried de-emphasis state as ``load`` + ``run_all``; returns like ``run_all``."""
-        self._ensure_engine()
         n = int(self._input_bandwidth)
         if len(input_signal) != n:
             raise ValueError("input_signal size and input_bandwidth mismatch")
         lib = _native.lib()
-        g = self._graph
-        if g is None or g["engine"] is not self._engine:
-            g = self._graph = {"engine": self._engine, "x": torch.empty(n, dtype=torch.complex64, device="cuda"),
-                               "graph": None, "warm": 0}
+        g = self._graph_state()
         src = input_signal if isinstance(input_signal, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(np.asarray(input_signal), dtype=np.complex64))
-        g["x"].copy_(src, non_blocking=True)
+        if not (src.is_cuda and src.data_ptr() == g["x"].data_ptr()):     # a block written straight into graph_input() needs no copy
+            g["x"].copy_(src, non_blocking=True)
         if g["graph"] is None and g["warm"] >= 1:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
