@@ -978,10 +978,10 @@ int rc_subband_combine(int device, int n_ranks, int64_t piece_len, int64_t n_inp
     const double m2n = -2.0 / (double)n_input;
     cudaError_t err;
     switch (n_ranks) {
-        case 2: err = launch_ew(piece_len / 2, 1, SubbandCombineEw<2>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
-        case 4: err = launch_ew(piece_len / 2, 1, SubbandCombineEw<4>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
-        case 8: err = launch_ew(piece_len / 2, 1, SubbandCombineEw<8>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
-        case 16: err = launch_ew(piece_len / 2, 1, SubbandCombineEw<16>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 2: err = launch_ew(piece_len, 1, SubbandCombineEw<2>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 4: err = launch_ew(piece_len, 1, SubbandCombineEw<4>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 8: err = launch_ew(piece_len, 1, SubbandCombineEw<8>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
+        case 16: err = launch_ew(piece_len, 1, SubbandCombineEw<16>{F, Y, piece_len, k0_base, m2n}, st, "tuner.subband_combine", bytes); break;
         default: return fail(RC_ERR_UNSUPPORTED, "subband_combine: 2, 4, 8 or 16 ranks");
     }
     RC_API_CUDA(err, "subband combine");
@@ -1016,10 +1016,10 @@ int rc_subband_combine_scatter(int device, int n_ranks, int64_t piece_len, int64
     if (const char* env = getenv("RC_SCATTER_CTAS")) cps = atoi(env);
     cudaError_t err;
     switch (n_ranks) {
-        case 2: err = launch_ew(piece_len / 2, 1, SubbandCombineScatterEw<2>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
-        case 4: err = launch_ew(piece_len / 2, 1, SubbandCombineScatterEw<4>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
-        case 8: err = launch_ew(piece_len / 2, 1, SubbandCombineScatterEw<8>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
-        case 16: err = launch_ew(piece_len / 2, 1, SubbandCombineScatterEw<16>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 2: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<2>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 4: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<4>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 8: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<8>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
+        case 16: err = launch_ew(piece_len, 1, SubbandCombineScatterEw<16>{F, piece_len, k0_base, m2n, tab}, st, "tuner.subband_combine_scatter", bytes, cps); break;
         default: return fail(RC_ERR_UNSUPPORTED, "subband_combine_scatter: 2, 4, 8 or 16 ranks");
     }
     RC_API_CUDA(err, "subband combine scatter");

@@ -559,51 +559,34 @@ struct StoreRealPart {
 // Twiddle W_N^{k0} from an fp64 sincospi, its powers by fp64 recurrence, rounded to fp32 once --
 // the same accuracy as the inter-pass twiddles of the FFT engine.
 // ---------------------------------------------------------------------------
-// A thread combines TWO adjacent k0 (j = 2 jj, 2 jj + 1; P is even): 16-byte loads of the pieces and
-// 16-byte stores of the bins -- over NVLink in the scattering variant, where larger contiguous
-// writes per warp (512 bytes) keep the links better fed than 8-byte ones.
-template <int G>
-RC_HD void subband_combine_pair(const float2* F, long long P, long long k0_base, double minus_two_over_n, long long j,
-                                float2* va, float2* vb) {
-    double sn, cs, sn2, cs2;
-    const double th = (double)(k0_base + j) * minus_two_over_n;
-#ifdef __CUDA_ARCH__
-    sincospi(th, &sn, &cs);
-    sincospi(th + minus_two_over_n, &sn2, &cs2);
-#else
-    sn = sin(kPi * th); cs = cos(kPi * th);
-    sn2 = sin(kPi * (th + minus_two_over_n)); cs2 = cos(kPi * (th + minus_two_over_n));
-#endif
-    const double2 w1a = make_double2(cs, sn), w1b = make_double2(cs2, sn2);
-    double2 wa = w1a, wb = w1b;
-    {
-        const float4 x = ldg4(F + j);
-        va[0] = make_float2(x.x, x.y);
-        vb[0] = make_float2(x.z, x.w);
-    }
-#pragma unroll
-    for (int g = 1; g < G; g++) {
-        const float4 x = ldg4(F + (long long)g * P + j);
-        va[g] = cmul(make_float2(x.x, x.y), make_float2((float)wa.x, (float)wa.y));
-        vb[g] = cmul(make_float2(x.z, x.w), make_float2((float)wb.x, (float)wb.y));
-        if (g + 1 < G) { wa = cmul64(wa, w1a); wb = cmul64(wb, w1b); }
-    }
-    Dft<G, -1>::run(va);
-    Dft<G, -1>::run(vb);
-}
-
+// (A two-bins-per-thread variant with 16-byte loads and stores was measured in round 2: the combine
+// alone got 7 % faster, but the overlapped step 6-9 % SLOWER at 2 and 8 GPUs -- one bin per thread kept.)
 template <int G>
 struct SubbandCombineEw {
-    const float2* F;      // [G][P], 16-byte aligned, P even
+    const float2* F;      // [G][P]
     float2* Y;            // [G][P]
     long long P, k0_base;
     double minus_two_over_n;
-    RC_HD void operator()(int, long long jj) const {      // launch over P / 2
-        float2 va[G], vb[G];
-        const long long j = 2 * jj;
-        subband_combine_pair<G>(F, P, k0_base, minus_two_over_n, j, va, vb);
+    RC_HD void operator()(int, long long j) const {
+        float2 v[G];
+        double sn, cs;
+        const double th = (double)(k0_base + j) * minus_two_over_n;
+#ifdef __CUDA_ARCH__
+        sincospi(th, &sn, &cs);
+#else
+        sn = sin(kPi * th); cs = cos(kPi * th);
+#endif
+        const double2 w1 = make_double2(cs, sn);
+        double2 w = w1;
+        v[0] = ldg(F + j);
 #pragma unroll
-        for (int k1 = 0; k1 < G; k1++) stg4(Y + (long long)k1 * P + j, va[k1], vb[k1]);
+        for (int g = 1; g < G; g++) {
+            v[g] = cmul(ldg(F + (long long)g * P + j), make_float2((float)w.x, (float)w.y));
+            if (g + 1 < G) w = cmul64(w, w1);
+        }
+        Dft<G, -1>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < G; k1++) Y[(long long)k1 * P + j] = v[k1];
     }
 };
 
@@ -623,24 +606,29 @@ struct SubbandCombineScatterEw {
     long long P, k0_base;
     double minus_two_over_n;
     ScatterTable tab;
-    RC_HD void operator()(int, long long jj) const {      // launch over P / 2
-        float2 va[G], vb[G];
-        const long long j = 2 * jj;
-        subband_combine_pair<G>(F, P, k0_base, minus_two_over_n, j, va, vb);
+    RC_HD void operator()(int, long long j) const {
+        float2 v[G];
+        double sn, cs;
+        const double th = (double)(k0_base + j) * minus_two_over_n;
+#ifdef __CUDA_ARCH__
+        sincospi(th, &sn, &cs);
+#else
+        sn = sin(kPi * th); cs = cos(kPi * th);
+#endif
+        const double2 w1 = make_double2(cs, sn);
+        double2 w = w1;
+        v[0] = ldg(F + j);
+#pragma unroll
+        for (int g = 1; g < G; g++) {
+            v[g] = cmul(ldg(F + (long long)g * P + j), make_float2((float)w.x, (float)w.y));
+            if (g + 1 < G) w = cmul64(w, w1);
+        }
+        Dft<G, -1>::run(v);
 #pragma unroll
         for (int k1 = 0; k1 < G; k1++) {
 #pragma unroll
-            for (int sgm = 0; sgm < kScatterSegs; sgm++) {
-                if (sgm >= tab.n[k1]) continue;
-                const long long lo = tab.lo[k1][sgm], hi = tab.hi[k1][sgm];
-                float2* d = tab.dst[k1][sgm] + (j - lo);
-                const bool in_a = j >= lo && j < hi, in_b = j + 1 >= lo && j + 1 < hi;
-                if (in_a && in_b && (((size_t)d) & 15) == 0) stg4(d, va[k1], vb[k1]);
-                else {
-                    if (in_a) d[0] = va[k1];
-                    if (in_b) d[1] = vb[k1];
-                }
-            }
+            for (int sgm = 0; sgm < kScatterSegs; sgm++)
+                if (sgm < tab.n[k1] && j >= tab.lo[k1][sgm] && j < tab.hi[k1][sgm]) tab.dst[k1][sgm][j - tab.lo[k1][sgm]] = v[k1];
         }
     }
 };
