@@ -17,7 +17,6 @@
 
 #include "../../include/radiocore_b200.h"
 #include "rc_exec.cuh"
-#include "rc_fuse_ad.cuh"
 
 #ifndef RC_EMULATE
 #include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges around the block-level entry points
@@ -225,8 +224,7 @@ struct DemodBank {
     float2 *Z1 = nullptr, *Z2 = nullptr, *ZpB = nullptr, *ZpA = nullptr, *w0 = nullptr, *w1 = nullptr;
     float *mpx = nullptr, *pilot = nullptr, *lmr = nullptr, *audio_tmp = nullptr;
 
-    // first_R_h: preferred length of the first pass of the B/2-point real FFT (0: planner's choice)
-    int init(int mode_, long long B_, long long A_, double tau_, int batch_, TableStore& store, Arena& arena, int first_R_h = 0) {
+    int init(int mode_, long long B_, long long A_, double tau_, int batch_, TableStore& store, Arena& arena) {
         mode = mode_; B = B_; A = A_; tau = tau_; batch = batch_;
         nch = mode == RC_MODE_WBFM ? 2 : 1;
         if (B < 2 || A < 2 || batch < 1) return fail(RC_ERR_INVALID, "demod: sizes must be >= 2 and batch >= 1");
@@ -236,7 +234,7 @@ struct DemodBank {
             return fail(RC_ERR_UNSUPPORTED, "demod: sizes must factor into 2^a 3^b 5^c");
         if (mode == RC_MODE_WBFM && B <= 3 * 41)
             return fail(RC_ERR_INVALID, "wbfm: input_size must exceed the filtfilt pad length (123)");
-        RC_API_CUDA(fft_plan_build(planBh, h, store, first_R_h), "plan B/2");
+        RC_API_CUDA(fft_plan_build(planBh, h, store), "plan B/2");
         RC_API_CUDA(fft_plan_build(planAh, hp, store), "plan A/2");
         const bool wb = mode == RC_MODE_WBFM;
         RC_API_CUDA(make_real_spec(specBA, B, A, true, false, arena), "spec B->A");
@@ -296,24 +294,18 @@ struct DemodBank {
         return run_from(LoadAnglePacked{ang, B}, 4.0 * B * batch, out, st);
     }
 
-    // the engine's fused seam kernel (rc_fuse_ad.cuh) has already run pass 0 of the discriminator's
-    // real FFT into w0: continue with pass 1
-    int run_after_pass0(float* out, cudaStream_t st) {
-        return run_from(LoadC64{w0, h}, 0.0, out, st, 1);
-    }
-
     template <class DiscLoad>
-    int run_from(const DiscLoad& disc, double disc_bytes, float* out, cudaStream_t st, int pass_begin = 0) {
+    int run_from(const DiscLoad& disc, double disc_bytes, float* out, cudaStream_t st) {
         if (mode != RC_MODE_WBFM) {
             // Decimate keeps bins k < m2 of the discriminator's spectrum; through the packed-real
             // algebra they depend on Z1[k] and Z1[h-k] only: skip the stores in between.
             long long lo = (specBA.m2 + 2) / 2 * 2, hi = (h - specBA.m2 - 1) / 2 * 2;
             if (hi < lo) hi = lo;
             RC_API_CUDA((fft_exec<-1>(planBh, batch, disc, StoreC64Win{Z1, h, lo, hi}, w0, w1, st,
-                                  "demod.rfft_disc", disc_bytes, 8.0 * (double)(h - (hi - lo)) * batch, pass_begin)), "fft discriminator");
+                                  "demod.rfft_disc", disc_bytes, 8.0 * (double)(h - (hi - lo)) * batch)), "fft discriminator");
         } else {
             RC_API_CUDA((fft_exec<-1>(planBh, batch, disc, StoreC64{Z1, h, 1.0f}, w0, w1, st,
-                                  "demod.rfft_disc", disc_bytes, 0.0, pass_begin)), "fft discriminator");
+                                  "demod.rfft_disc", disc_bytes, 0.0)), "fft discriminator");
         }
         if (mode != RC_MODE_WBFM) {
             RC_API_CUDA(launch_ew(hp, batch, SpecResampleEw{specBA, Z1, ZpA}, st, "demod.spec_resample",
@@ -382,7 +374,6 @@ struct rc_engine {
         std::vector<int> members;
         long long* d_roll = nullptr;
         float* ang = nullptr;                   // angle(y)/pi of every channel sample (StoreAngle)
-        bool fuse_ad = false;                   // last IFFT pass + discriminator + first real-FFT pass in one kernel
         float2 *w0 = nullptr, *w1 = nullptr;
         long long audio_offset = 0;
     };
@@ -487,17 +478,9 @@ int rc_engine_commit(rc_engine* e) {
         auto& bk = *bp;
         auto& c0 = e->chans[bk.members[0]];
         const int batch = (int)bk.members.size();
-        bk.planB = &e->planB[c0.B];
-        // the seam kernel needs the inverse FFT to END with the R = 100, 32-column schedule and the real
-        // FFT to START with R = 100: ask the planner for such a split of B/2 (it falls back if there is none)
-        const FftPlan& pb = *bk.planB;
-        const bool want_fuse = getenv("RC_NO_FUSE_AD") == nullptr && pb.nfast >= 2 && pb.n < (1LL << 31) &&
-                               pb.fast[pb.nfast - 1].fast_id == 24 && pb.fast[pb.nfast - 1].R == kFuseR;
-        int rc = bk.demod.init(c0.mode, c0.B, c0.A, c0.tau, batch, e->store, e->arena, want_fuse ? kFuseR : 0);
+        int rc = bk.demod.init(c0.mode, c0.B, c0.A, c0.tau, batch, e->store, e->arena);
         if (rc) return rc;
-        const FftPlan& ph = bk.demod.planBh;
-        bk.fuse_ad = want_fuse && ph.nfast >= 2 && ph.fast[0].fast_id == 0 && ph.fast[0].R == kFuseR &&
-                     pb.fast[pb.nfast - 1].stride == 2 * ph.fast[0].stride;
+        bk.planB = &e->planB[c0.B];
         std::vector<long long> rolls;
         for (int m : bk.members) rolls.push_back(e->shifted_roll(e->chans[m].roll));
         RC_API_CUDA(e->arena.upload(&bk.d_roll, rolls), "rolls");
@@ -599,29 +582,6 @@ int rc_engine_run(rc_engine* e, float* audio_dev, void* stream) {
         auto& bk = *bp;
         const long long B = bk.demod.B;
         const int batch = bk.demod.batch;
-        const int np = bk.planB->nfast;
-        float2* last_src = np >= 2 ? (((np - 2) % 2 == 0) ? bk.w0 : bk.w1) : nullptr;
-        FuseAdArgs fa;
-        bool fuse = bk.fuse_ad;
-        if (fuse) {
-            fa.PA = bk.planB->fast[np - 1];
-            fa.PB = bk.demod.planBh.fast[0];
-            fa.stB = StoreC64{bk.demod.w0, bk.demod.h, 1.0f};
-            fuse = v3_fuse_ad_possible(fa.PA, fa.PB, LoadC64{last_src, B}, batch);
-        }
-        if (fuse) {
-            // passes 0 .. np-2 of the channel IFFT, then the seam kernel, then the real FFT from pass 1
-            RC_API_CUDA((fft_exec<+1>(*bk.planB, batch, tuner_gather(e, bk.d_roll, B), StoreAngle{bk.ang, B},
-                                      bk.w0, bk.w1, st, "tuner.channel_ifft", 8.0 * B * batch, 4.0 * B * batch, 0, np - 2)),
-                        "tuner channel ifft");
-            {
-                ProfileScope scope("tuner.channel_ifft+demod.rfft_disc/fused_seam_R100", 8.0 * B * batch + 8.0 * bk.demod.h * batch, st);
-                RC_API_CUDA(v3_run_fuse_ad(fa, LoadC64{last_src, B}, batch, st), "fused seam");
-            }
-            int rc = bk.demod.run_after_pass0(audio_dev + bk.audio_offset, st);
-            if (rc) return rc;
-            continue;
-        }
         RC_API_CUDA((fft_exec<+1>(*bk.planB, batch, tuner_gather(e, bk.d_roll, B), StoreAngle{bk.ang, B},
                                   bk.w0, bk.w1, st, "tuner.channel_ifft", 8.0 * B * batch, 4.0 * B * batch)),   // DRAM bytes: the Hann table stays in L2
                     "tuner channel ifft");

@@ -185,21 +185,17 @@ cudaError_t fft_generic_pass(const FftPass& P, int batch, const LD& ld, const ST
 // out_bytes feed the optional profiler: compulsory bytes the first pass reads
 // through LoadOp and the last pass writes through StoreOp (0 -> 8 bytes per
 // element, i.e. a plain complex64 array).
-// pass_begin / pass_end (inclusive, -1 = last) run a sub-range of the passes: pass i > 0 reads the
-// ping-pong buffer pass i-1 wrote (work0 for even i-1), so a caller may replace a pass by its own
-// kernel (rc_fuse_ad.cuh) and run the passes on either side of it.
 template <int SIGN, class LoadOp, class StoreOp>
 cudaError_t fft_exec(const FftPlan& plan, int batch, const LoadOp& ld, const StoreOp& st,
                      float2* work0, float2* work1, cudaStream_t stream, const char* tag = "fft",
-                     double in_bytes = 0.0, double out_bytes = 0.0, int pass_begin = 0, int pass_end = -1) {
+                     double in_bytes = 0.0, double out_bytes = 0.0) {
     if (batch <= 0) return cudaSuccess;
     constexpr bool v3ok = V3LoadOk<LoadOp>::value && V3StoreOk<StoreOp>::value;
     const bool fast = v3ok && plan.nfast >= 2 && plan.n < (1LL << 31);
     const int npass = fast ? plan.nfast : plan.npass;
     const FftPass* passes = fast ? plan.fast : plan.pass;
     const double plain = 8.0 * (double)plan.n * (double)batch;
-    if (pass_end < 0 || pass_end > npass - 1) pass_end = npass - 1;
-    for (int i = pass_begin; i <= pass_end; i++) {
+    for (int i = 0; i < npass; i++) {
         const FftPass& P = passes[i];
         const bool first = i == 0, last = i == npass - 1;
         float2* src = ((i - 1) % 2 == 0) ? work0 : work1;

@@ -789,13 +789,11 @@ inline bool fft_tuned_split(long long n, std::vector<int>& Rs) {
 
 // Split n into 2..4 curated pass lengths of least estimated cost; false when n has no such split.
 // RC_FFT_SPLIT="n:r0xr1x..;n:..." forces a split (kernel experiments).
-// first_R > 0: only splits whose first pass has that length (the fused seam of rc_fuse_ad.cuh wants the
-// real FFT to start with R = 100)
-inline bool fft_choose_fast(long long n, std::vector<int>& Rs, int first_R = 0) {
+inline bool fft_choose_fast(long long n, std::vector<int>& Rs) {
     std::vector<int> cur;
     int max_r = 1 << 30;
     if (const char* env = getenv("RC_FFT_MAXR")) max_r = atoi(env);      // experiments: cap the pass length
-    if (const char* env = first_R > 0 ? nullptr : getenv("RC_FFT_SPLIT")) {
+    if (const char* env = getenv("RC_FFT_SPLIT")) {
         std::string e(env);
         size_t pos = 0;
         while (pos < e.size()) {
@@ -821,7 +819,7 @@ inline bool fft_choose_fast(long long n, std::vector<int>& Rs, int first_R = 0) 
             if (r.size() >= 2 && r.size() <= (size_t)kMaxPasses && prod == n) { Rs = r; return true; }
         }
     }
-    if (first_R <= 0 && max_r == (1 << 30) && fft_tuned_split(n, Rs)) return true;
+    if (max_r == (1 << 30) && fft_tuned_split(n, Rs)) return true;
     for (const V3Entry& e : v3_table())
         if (n % e.R() == 0 && e.R() <= max_r && e.role != 2 && v3_has(e.R())) cur.push_back(e.R());
     double best = 1e30;
@@ -848,7 +846,6 @@ inline bool fft_choose_fast(long long n, std::vector<int>& Rs, int first_R = 0) 
         if (depth == kMaxPasses) return;
         for (int c : cur) {
             if (rest % c) continue;
-            if (depth == 0 && first_R > 0 && c != first_R) continue;
             r.push_back(c);
             rec(rest / c, depth + 1);
             r.pop_back();
@@ -859,7 +856,7 @@ inline bool fft_choose_fast(long long n, std::vector<int>& Rs, int first_R = 0) 
     return !pick.empty();
 }
 
-inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store, int first_R = 0) {
+inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store) {
     if (!fft_size_supported(n)) return cudaErrorInvalidValue;
     std::vector<int> Rs;
     int T = 1;
@@ -874,7 +871,7 @@ inline cudaError_t fft_plan_build(FftPlan& plan, long long n, TableStore& store,
     }
     plan.nfast = 0;
     std::vector<int> Fs;
-    if ((first_R > 0 && fft_choose_fast(n, Fs, first_R)) || fft_choose_fast(n, Fs)) {
+    if (fft_choose_fast(n, Fs)) {
         plan.nfast = (int)Fs.size();
         Ns = 1;
         for (int i = 0; i < plan.nfast; i++) {

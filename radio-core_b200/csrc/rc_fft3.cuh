@@ -38,7 +38,7 @@ namespace rc {
 template <int R0_, int R1_, int R2_, int NT_, int MINB_, int CP_ = 8>
 struct V3Sched {
     static constexpr int R0 = R0_, R1 = R1_, R2 = R2_, NT = NT_, MINB = MINB_;
-    static constexpr int CP = CP_, T = 2 * CP_, LOGCP = CP_ == 1 ? 0 : (CP_ == 8 ? 3 : (CP_ == 16 ? 4 : 5));
+    static constexpr int CP = CP_, T = 2 * CP_, LOGCP = CP_ == 8 ? 3 : (CP_ == 16 ? 4 : 5);
     static constexpr int R = R0_ * R1_ * R2_;
     static constexpr int U = R1_ * R2_;
     static constexpr int NG = NT_ / CP_;                     // row groups working in parallel
@@ -53,7 +53,7 @@ struct V3Sched {
     static constexpr int WIN_OFF = (SMEM_BYTES + 127) / 128 * 128;  // tuner gather by TMA: + [R][T] Hann weights
     static constexpr int SMEM_BYTES_WIN = WIN_OFF + R * T * 4;
     static constexpr int SMEM_BYTES_ANG = WIN_OFF + R * 4;          // angle tile by TMA: + one preceding sample per row
-    static_assert(CP_ == 1 || CP_ == 8 || CP_ == 16 || CP_ == 32, "8, 16 or 32 column pairs (1: the halo pair of rc_fuse_ad.cuh)");
+    static_assert(CP_ == 8 || CP_ == 16 || CP_ == 32, "8, 16 or 32 column pairs");
     static_assert(NT_ % CP_ == 0, "threads must be a multiple of the column pairs");
     static_assert(T * PITCH <= TILE_F4 * 2, "transposed layout must fit the tile buffer");
 };

@@ -189,45 +189,3 @@ def test_sharded_load_fused_stores_replay(emu, world):
         emu.subband_combine_scatter(R[p], N, p * plan.p, segs)
     for d in range(world):
         assert np.array_equal(subs[d], want[d]), d
-
-
-@pytest.mark.parametrize("N,B,A,C_,kind", [(128_000, 16_000, 3_200, 8, "MFM"), (96_000, 16_000, 4_000, 5, "FM"),
-                                            (3_000_000, 1_000_000, 48_000, 2, "FM")])
-def test_fused_seam_replay(emu, N, B, A, C_, kind, monkeypatch):
-    """rc_fuse_ad.cuh (last IFFT pass -> angle -> discriminator -> first real-FFT pass in one kernel):
-    active for channel sizes whose inverse FFT ends with the R = 100 / 32-column schedule (16 000 =
-    160 x 100; 1 000 000 = 200 x 50 x 100, the config-3 channel).  Checked against the oracle, against
-    the unfused kernels (RC_NO_FUSE_AD=1) and -- by the launch counter -- that the fused path really ran.
-    Covers tile 0 (its halo is the previous row's last column), ragged last tiles (10 000 columns are
-    not a multiple of 32) and two blocks of carried state."""
-    import radiocore_oracle as oracle
-    from bench_support import synth
-    offs = synth.tiling_centers(N, C_, B)
-    o = oracle.Tuner()
-    for off in offs:
-        o.add_channel(1e8 + off, B, getattr(oracle, kind)(B, A))
-    o.request_bandwidth(N)
-    outs, launches = {}, {}
-    for fused in (True, False):
-        if not fused:
-            monkeypatch.setenv("RC_NO_FUSE_AD", "1")
-        t = emu.Tuner()
-        for off in offs:
-            t.add_channel(1e8 + off, B, getattr(emu, kind)(B, A))
-        t.request_bandwidth(N)
-        n0 = emu.lib().rc_profile_launches()
-        res = []
-        for blk in range(2):
-            x = synth.wideband(N, offs, B, seed=5, block=blk, deviation=min(0.3 * B, 75e3))
-            t.load(x)
-            res.append(t.run_all())
-            if fused:
-                o.load(x)
-                for c in range(C_):
-                    ref = o.channels()[c].demodulator.run(o.run(c))
-                    parity.assert_parity(res[-1][c], ref, f"fused seam B={B} blk{blk} ch{c}")
-        outs[fused], launches[fused] = res, emu.lib().rc_profile_launches() - n0
-    assert launches[True] == launches[False] - 2, launches            # one launch fewer per block: the seam is one kernel
-    for blk in range(2):
-        for c in range(C_):
-            assert np.max(np.abs(outs[True][blk][c] - outs[False][blk][c])) <= 2e-6 * np.max(np.abs(outs[False][blk][c]))
