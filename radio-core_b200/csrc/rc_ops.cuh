@@ -940,7 +940,6 @@ RC_HD int fold_slot(int i) { return i + 4 * (i >> 5); }
 constexpr int kFoldWin = kFirChunk + 2 * kFoldK + 16;
 static __global__ void __launch_bounds__(kFirThreads) filtfilt_fold_kernel(const FiltFiltEw f, const __grid_constant__ FirTapsParam ctaps) {
     __shared__ __align__(16) float xf[kFoldWin + 4 * (kFoldWin / 32) + 8];
-    __shared__ __align__(16) float xg[kFoldWin + 4 * (kFoldWin / 32) + 8];
     __shared__ double xs[kFirSlots];
     __shared__ double tp[kFirMaxTaps];
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -968,9 +967,7 @@ static __global__ void __launch_bounds__(kFirThreads) filtfilt_fold_kernel(const
         }
         return;
     }
-    // window[i] = x[n0 - 40 + i], i in [0, 1024 + 80): 16-byte loads where the source allows.  A second
-    // copy shifted by one sample (xg[i] = x[i + 1]) makes every ODD-aligned sample pair an aligned
-    // 8-byte shared-memory element too, so that the arithmetic below runs on packed register pairs.
+    // window[i] = x[n0 - 40 + i], i in [0, 1024 + 80): 16-byte loads where the source allows
     const float* src = xb + (n0 - kFoldK);
     if ((((size_t)src) & 15) == 0) {
         for (int i = tid; i < (kFirChunk + 2 * kFoldK) / 4; i += kFirThreads)
@@ -978,61 +975,41 @@ static __global__ void __launch_bounds__(kFirThreads) filtfilt_fold_kernel(const
     } else {
         for (int i = tid; i < kFirChunk + 2 * kFoldK; i += kFirThreads) xf[fold_slot(i)] = __ldg(src + i);
     }
-    for (int i = tid; i < kFirChunk + 2 * kFoldK - 1; i += kFirThreads) xg[fold_slot(i)] = __ldg(src + i + 1);
     __syncthreads();
-    // Outputs r, r+1 (r even) of tap distance d share one FADD2 + one FFMA2 (sm_100 packed fp32): the
-    // pair of left samples (x[n-d+r], x[n-d+r+1]) starts at an even window index for odd jj (copy xf,
-    // "E" pairs) and at an odd one for even jj (copy xg, "O" pairs); likewise on the right.  Each
-    // output still sees exactly the scalar sequence of FiltFiltEw::folded (bit-identical results).
     const int c = tid * kFirPer + kFoldK;          // window index of this thread's first output (multiple of 8)
-    float2 lwE[8], lwO[8], rwE[8], rwO[8];         // pair k of a window = elements (2k, 2k+1) [E] or (2k+1, 2k+2) [O]
-    auto load4 = [&](const float* base, int idx, float2* dst) {
-        const float4 a = *(const float4*)(base + fold_slot(idx)), d = *(const float4*)(base + fold_slot(idx + 4));
-        dst[0] = make_float2(a.x, a.y); dst[1] = make_float2(a.z, a.w);
-        dst[2] = make_float2(d.x, d.y); dst[3] = make_float2(d.z, d.w);
-    };
-    load4(xf, c, lwE + 4);
-    load4(xg, c, lwO + 4);
-#pragma unroll
-    for (int k = 0; k < 4; k++) { rwE[k] = lwE[4 + k]; rwO[k] = lwO[4 + k]; }
+    float lw[16], rw[16];
+    {
+        const float4 a = *(const float4*)(xf + fold_slot(c)), d = *(const float4*)(xf + fold_slot(c + 4));
+        lw[8] = rw[0] = a.x; lw[9] = rw[1] = a.y; lw[10] = rw[2] = a.z; lw[11] = rw[3] = a.w;
+        lw[12] = rw[4] = d.x; lw[13] = rw[5] = d.y; lw[14] = rw[6] = d.z; lw[15] = rw[7] = d.w;
+    }
     double acc[kFirPer];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        acc[2 * q] = f.fold.gc * (double)rwE[q].x;
-        acc[2 * q + 1] = f.fold.gc * (double)rwE[q].y;
-    }
+    for (int r = 0; r < kFirPer; r++) acc[r] = f.fold.gc * (double)rw[r];
 #pragma unroll
     for (int m = 0; m < kFoldK / kFoldGroup; m++) {
-        // left window = x[c - 8(m+1) .. +15]: its upper half is the previous group's lower half;
-        // right window = x[c + 8m .. +15]: its lower half is the previous group's upper half
-        if (m > 0) {
+        // left window: x[c - 8(m+1) .. +15], its upper half is the previous group's lower half;
+        // right window: x[c + 8m .. +15], its lower half is the previous group's upper half
 #pragma unroll
-            for (int k = 0; k < 4; k++) { lwE[4 + k] = lwE[k]; lwO[4 + k] = lwO[k]; rwE[k] = rwE[4 + k]; rwO[k] = rwO[4 + k]; }
+        for (int i = 0; i < 8; i++) { lw[8 + i] = m == 0 ? lw[8 + i] : lw[i]; rw[i] = m == 0 ? rw[i] : rw[8 + i]; }
+        {
+            const int lb = c - 8 * (m + 1), rb = c + 8 * m + 8;
+            const float4 a = *(const float4*)(xf + fold_slot(lb)), d = *(const float4*)(xf + fold_slot(lb + 4));
+            lw[0] = a.x; lw[1] = a.y; lw[2] = a.z; lw[3] = a.w; lw[4] = d.x; lw[5] = d.y; lw[6] = d.z; lw[7] = d.w;
+            const float4 e = *(const float4*)(xf + fold_slot(rb)), h = *(const float4*)(xf + fold_slot(rb + 4));
+            rw[8] = e.x; rw[9] = e.y; rw[10] = e.z; rw[11] = e.w; rw[12] = h.x; rw[13] = h.y; rw[14] = h.z; rw[15] = h.w;
         }
-        load4(xf, c - 8 * (m + 1), lwE);
-        load4(xg, c - 8 * (m + 1), lwO);
-        load4(xf, c + 8 * m + 8, rwE + 4);
-        load4(xg, c + 8 * m + 8, rwO + 4);
-        float2 sg[4];
+        float sg[kFirPer];
 #pragma unroll
-        for (int q = 0; q < 4; q++) sg[q] = make_float2(0.f, 0.f);
+        for (int r = 0; r < kFirPer; r++) sg[r] = 0.f;
 #pragma unroll
         for (int jj = 0; jj < kFoldGroup; jj++) {
             const float g = f.fold.g[8 * m + 1 + jj];
-            const float2 g2 = make_float2(g, g);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                // left elements 7 - jj + 2q (+1), right elements 1 + jj + 2q (+1) of the 16-element windows
-                const float2 L = (jj & 1) ? lwE[(7 - jj + 2 * q) / 2] : lwO[(6 - jj + 2 * q) / 2];
-                const float2 Rr = (jj & 1) ? rwE[(1 + jj + 2 * q) / 2] : rwO[(jj + 2 * q) / 2];
-                sg[q] = __ffma2_rn(g2, __fadd2_rn(L, Rr), sg[q]);
-            }
+            for (int r = 0; r < kFirPer; r++) sg[r] = fold_mul_add(g, lw[7 - jj + r], rw[1 + jj + r], sg[r]);
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            acc[2 * q] += (double)sg[q].x;
-            acc[2 * q + 1] += (double)sg[q].y;
-        }
+        for (int r = 0; r < kFirPer; r++) acc[r] += (double)sg[r];
     }
     float* o = f.out + (long long)b * f.n + n0 + tid * kFirPer;
     if ((((size_t)o) & 15) == 0) {
