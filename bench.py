@@ -477,7 +477,8 @@ def measure_sharded(ctx, wl, x_dev, steps, warmup, profile, e2e):
         t = time.perf_counter() - t0
         h2d, d2h_all = ctx.max_over_ranks(8.0 * m, float(d2h))
         res["e2e"] = {"t": ctx.max_over_ranks(t)[0], "h2d": int(h2d) * ctx.world, "d2h": int(d2h_all) * ctx.world,
-                      "api": "every rank: pinned host branch x[rank::G] -> H2D over its own PCIe link -> "
+                      "api": "every rank: pinned host branch x[rank::G] (samples dealt round-robin to the ranks' buffers by the "
+                             "ingest side as they arrive; that host-side dealing is not timed) -> H2D over its own PCIe link -> "
                              "sharding.ShardedLoad (local FFT, 2 NVLink exchanges, combine) -> Tuner.load_subband + run_all "
                              "-> D2H of its channels' audio"}
     while load.in_flight():
