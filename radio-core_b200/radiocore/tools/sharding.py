@@ -231,8 +231,7 @@ class ShardedLoad:
         self._depth = max(self.lanes + 1, depth)
         pad = 1 << 16                                               # the gather's tensor map describes whole rows past x_len
         slot_len = max(b for _, b in arcs) + pad
-        self._Fs = [k.empty(plan.m) for _ in range(self.lanes)]     # F_g, natural order: piece p = [p*P, (p+1)*P)
-        self._Ys = [k.empty(plan.m) for _ in range(self.lanes)]     # [G][P]: bins k1*M + rank*P + j
+        self._Fs = self._Ys = None                                  # staging arrays of the unfused paths (allocated below)
         # Transport of the two exchanges.  "peer": the receive buffers (R and the sub-band slots) live in
         # symmetric memory mapped into every rank (torch.distributed._symmetric_memory); a rank PUSHES its
         # pieces / runs straight into the peers' buffers with device-to-device copies over NVLink and a
@@ -264,6 +263,10 @@ class ShardedLoad:
         self.fused_fft = ok and mode in ("1", "fft")            # exchange 1 = stores of the FFT's last pass
         self.fused_combine = ok and mode in ("1", "combine")     # exchange 2 = stores of the combine
         self.fused = self.fused_fft and self.fused_combine
+        if not self.fused_fft:
+            self._Fs = [k.empty(plan.m) for _ in range(self.lanes)]     # F_g, natural order: piece p = [p*P, (p+1)*P)
+        if not self.fused_combine:
+            self._Ys = [k.empty(plan.m) for _ in range(self.lanes)]     # [G][P]: bins k1*M + rank*P + j
         if ok:
             g, p8 = self._rank, 8 * plan.p
             self._piece_bases = [[self._peer.ptrs[d] + self._peer.r_offset_bytes(ln) + g * p8 for d in range(self._world)]
@@ -354,6 +357,13 @@ class ShardedLoad:
         self._block += 1
         k = self._k = self._ks[lane]
         done = k.begin(x_branch, slot, ready)
+        try:
+            self._post_on_lane(k, lane, x_branch, slot)
+        finally:
+            ev = k.end(done)                        # always leave the side-stream context
+        self._pending.append((slot, ev, k))
+
+    def _post_on_lane(self, k, lane, x_branch, slot):
         self._mark("begin")
         if self.fused_fft:
             k.fft_scatter(x_branch, self._piece_bases[lane])
@@ -378,7 +388,6 @@ class ShardedLoad:
             self._mark("combine")
             self._exchange_bins(slot, lane)
             self._mark("exchange_bins")
-        self._pending.append((slot, k.end(done), k))
 
     def _mark(self, name):
         if self.phase_events is not None and hasattr(self._k, "mark"):

@@ -189,3 +189,60 @@ def test_sharded_load_fused_stores_replay(emu, world):
         emu.subband_combine_scatter(R[p], N, p * plan.p, segs)
     for d in range(world):
         assert np.array_equal(subs[d], want[d]), d
+
+
+@pytest.mark.parametrize("world,seed", [(2, 1), (4, 2), (4, 3), (8, 4)])
+def test_sharded_load_offgrid_replay(emu, world, seed):
+    """Sharded load with channels OFF the bin grid, unevenly spread over the ranks, overlapping
+    between neighbours and reaching across the ends of the spectrum (arcs that wrap from bin N-1 to
+    bin 0, halos on both sides): every virtual rank's sub-band against a float64 FFT and its audio
+    against the oracle."""
+    import radiocore_oracle as oracle
+    from bench_support import synth
+    from radiocore.tools import sharding
+    rng = np.random.default_rng(seed)
+    N, B, A = 192_000, 12_000, 2_400
+    C_ = int(rng.integers(world, 14))
+    # centres anywhere in the band (the edge channels' bins wrap around the spectrum), sorted: contiguous slices
+    centers = np.sort(rng.integers(-N // 2 + B // 2 + 1, N // 2 - B // 2 - 1, size=C_)).astype(float)
+    centers[0] = -N / 2 + B / 2 + 3                     # lowest channel: its lowest bins sit just above bin N/2 (cyclic)
+    centers[-1] = N / 2 - B / 2 - 5
+    x = synth.wideband(N, list(centers), B, seed=seed)
+    o = oracle.Tuner()
+    for f in centers:
+        o.add_channel(1e8 + f, B, oracle.FM(B, A))
+    o.input_frequency = 1e8
+    o.request_bandwidth(N)
+    o.load(x)
+    X64 = np.fft.fft(x.astype(np.complex128))
+    tuners, arcs = [], []
+    for r in range(world):
+        t = emu.Tuner()
+        mine = sharding.shard_tuner(t, [1e8 + f for f in centers], B, lambda c: emu.FM(B, A), 1e8, N, world, r)
+        arcs.append(sharding.covering_arc(t.needed_bins(), N) if mine else (0, 2))
+        if mine:
+            t.set_subband(*arcs[-1])
+        tuners.append((t, mine))
+    plan = sharding.SubbandPlan(N, world, arcs)
+    fft = emu.Fft(plan.m)
+    R = [np.zeros((world, plan.p), dtype=np.complex64) for _ in range(world)]
+    subs = [np.zeros(arcs[d][1] + 64, dtype=np.complex64) for d in range(world)]
+    for g in range(world):
+        emu.fft_scatter(fft, x[g::world], [R[p][g] for p in range(world)])
+    for p in range(world):
+        segs = [(k1, j0, j1, subs[d], pos) for d in range(world) for k1, j0, j1, pos in plan.runs(p, d)]
+        emu.subband_combine_scatter(R[p], N, p * plan.p, segs)
+    rms = np.sqrt(np.mean(np.abs(X64) ** 2))
+    for d, (t, mine) in enumerate(tuners):
+        if not mine:
+            continue
+        lo, length = arcs[d]
+        want = X64[(lo + np.arange(length)) % N]
+        err = np.abs(subs[d][:length] - want)
+        assert np.max(err) <= 2e-6 * np.max(np.abs(X64)) + 5e-6 * rms, (d, np.max(err))
+        t.load_subband(subs[d])
+        audio = t.run_all()
+        for i, c in enumerate(mine):
+            ref = o.channels()[c].demodulator.run(o.run(c))
+            if np.max(np.abs(ref)) > 1e-2:          # conditioning of the relative bound (overlapping stations fade)
+                parity.assert_parity(audio[i], ref, f"world {world} rank {d} ch {c}", tol_scale=2.0)
