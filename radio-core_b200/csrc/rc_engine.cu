@@ -218,7 +218,6 @@ struct DemodBank {
     float zi0[50];
     float* d_taps = nullptr;
     double* d_zi = nullptr; double* d_zi_next = nullptr;
-    double* d_stage = nullptr; double* d_partial = nullptr;
     double* d_g = nullptr; int gK = 0;
     std::vector<double> g_host;
     float2 *Z1 = nullptr, *Z2 = nullptr, *ZpB = nullptr, *ZpA = nullptr, *w0 = nullptr, *w1 = nullptr;
@@ -250,8 +249,6 @@ struct DemodBank {
             RC_API_CUDA(arena.upload(&d_taps, t), "taps");
             RC_API_CUDA(arena.alloc(&d_zi, (size_t)batch * nch * 50), "zi");
             RC_API_CUDA(arena.alloc(&d_zi_next, (size_t)batch * nch * 50), "zi_next");
-            RC_API_CUDA(arena.alloc(&d_stage, (size_t)batch * nch * A), "stage");
-            RC_API_CUDA(arena.alloc(&d_partial, (size_t)batch * nch * epi_chunks(A)), "partial");
             int rc = reset_state();
             if (rc) return rc;
         }
@@ -340,8 +337,8 @@ struct DemodBank {
         }
         EpilogueParams p;
         p.in = audio_tmp; p.out = out; p.zi = d_zi; p.zi_next = d_zi_next; p.taps = d_taps;
-        p.stage = d_stage; p.partial = d_partial;
         p.A = A; p.nch = nch; p.ntaps = 51; p.deemph = 1; p.dc_clip = 1;
+        p.dc = ZpA; p.dc_stride = hp; p.dc_scale = (double)hp;      // bin 0 of every audio channel's packed spectrum
         RC_API_CUDA(launch_epilogue(p, batch, st, taps), "epilogue");
         // carried state: copied back rather than swapping the two pointers, so that a captured
         // CUDA graph of the block (fixed kernel arguments) carries it correctly when replayed
@@ -808,8 +805,8 @@ int rc_deemph_run(rc_deemph* d, const float* in, float* outp, void* stream) {
     DeviceGuard g(d->device);
     EpilogueParams p;
     p.in = in; p.out = outp; p.zi = d->d_zi; p.zi_next = d->d_zi_next; p.taps = d->d_taps;
-    p.stage = nullptr; p.partial = nullptr;
     p.A = d->size; p.nch = 1; p.ntaps = 51; p.deemph = 1; p.dc_clip = 0;
+    p.dc = nullptr; p.dc_stride = 0; p.dc_scale = 0.0;
     RC_API_CUDA(launch_epilogue(p, 1, (cudaStream_t)stream, d->taps), "deemph");
     RC_API_CUDA(dev_copy(d->d_zi, d->d_zi_next, 50 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "zi carry");
     return RC_OK;

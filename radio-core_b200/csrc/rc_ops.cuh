@@ -712,14 +712,41 @@ struct EpilogueParams {
     float* out;           // [batch][A][nch]   interleaved, final
     double* zi;           // [batch][nch][K]   carried filter state (K = ntaps-1)
     double* zi_next;      // scratch of the same shape
-    double* stage;        // [batch][nch][A]   filtered audio before mean removal (dc_clip only)
-    double* partial;      // [batch][nch][chunks] per-chunk sums (dc_clip only)
     const float* taps;    // ntaps FIR taps (float32 values, as the reference stores them)
     long long A;
     int nch, ntaps;
     int deemph;           // 0: no filter (plain FM)
     int dc_clip;          // 1: subtract block mean and clip to +-0.999
+    // dc_clip: bin 0 of the packed inverse-FFT input of every audio channel ([batch*nch] complex64 at
+    // stride dc_stride), from which the block sum of `in` follows without reading the block:
+    // sum_n in[n] = dc_scale * (re + im)   (packed real transform: sum_i z[i] = hp * Z'[0])
+    const float2* dc;
+    long long dc_stride;
+    double dc_scale;
 };
+
+// Block mean WITHOUT a pass over the filtered block (mfm.py:64, wbfm.py:97: `x - mean(x)` over the whole
+// block, both stereo channels together).  With y = lfilter(b, 1, a, zi):
+//   sum_n y[n] = sum_k b[k] * (S - T_k) + sum_{n<K} zi[n],   S = sum(a),  T_k = sum of the last k samples of a
+//             = S * c[0] - sum_{m=1..K} a[A-m] * c[m] + sum zi,          c[m] = sum_{k>=m} b[k]
+// -- S comes from bin 0 of the spectrum the audio was synthesised from, the rest is K = 50 samples and the
+// carried state, so every CTA of the FIR kernel can subtract the mean and clip in the same pass: the
+// fp64 staging array and the second kernel of round 1 are gone.  (The mean so obtained differs from
+// the mean of the rounded samples by ~1e-10 of full scale.)
+struct FirSuffixParam { double c[56]; };       // c[m] = sum_{k >= m} taps[k], m <= K
+
+RC_HD double epi_channel_sum_lane(const EpilogueParams& p, const FirSuffixParam& sp, long long bc, int lane, int nlanes) {
+    const float* a = p.in + bc * p.A;
+    const int K = p.deemph ? p.ntaps - 1 : 0;
+    double acc = 0.0;
+    for (int m = 1 + lane; m <= K && m <= p.A; m += nlanes) acc -= (double)a[p.A - m] * sp.c[m];
+    for (int n = lane; n < K && n < p.A; n += nlanes) acc += p.zi[bc * K + n];
+    if (lane == 0) {
+        const float2 z = ldg(p.dc + bc * p.dc_stride);
+        acc += p.dc_scale * ((double)z.x + (double)z.y) * sp.c[0];
+    }
+    return acc;
+}
 
 RC_HD double epi_fir(const EpilogueParams& p, int b, int ch, long long n) {
     const float* a = p.in + ((long long)b * p.nch + ch) * p.A;
@@ -827,12 +854,13 @@ __device__ __forceinline__ void fir_window8(const double* xs, const double* taps
     else fir_window8_t<0>(xs, taps, ntaps8, o, acc);
 }
 
-// Phase 1 of the audio epilogue: de-emphasis FIR of one chunk, fp64 staging, per-chunk sum.
+// The audio epilogue in ONE kernel: de-emphasis FIR of one chunk, block mean (analytic), clip, interleave.
 static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const EpilogueParams p, int nchunks,
-                                                                     const __grid_constant__ FirTapsParam ctaps) {
+                                                                     const __grid_constant__ FirTapsParam ctaps,
+                                                                     const __grid_constant__ FirSuffixParam suffix) {
     __shared__ double xs[kFirSlots];
     __shared__ double tp[kFirMaxTaps];
-    __shared__ double red[kFirThreads / 32];
+    __shared__ double mean_s;
     const int bc = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const int K = p.deemph ? p.ntaps - 1 : 0;
     const int ntaps8 = p.deemph ? (p.ntaps + 7) / 8 * 8 : 8;
@@ -849,6 +877,15 @@ static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const Epilo
         else if (i == 0) t = 1.0;
         tp[i] = t;
     }
+    const int bq = bc / p.nch, chq = bc - bq * p.nch;
+    if (p.dc_clip && tid < 32) {
+        // warp 0: the block mean of this channel (all nch audio channels together), analytically
+        double t = 0.0;
+        for (int ch = 0; ch < p.nch; ch++) t += epi_channel_sum_lane(p, suffix, (long long)bq * p.nch + ch, tid, 32);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+        if (tid == 0) mean_s = t / (double)(p.A * p.nch);
+    }
     __syncthreads();
     double acc[kFirPer];
 #pragma unroll
@@ -856,53 +893,20 @@ static __global__ void __launch_bounds__(kFirThreads) epi_fir_kernel(const Epilo
     const int o = tid * kFirPer;
     if (ctaps.n8 == 56 && ntaps8 == 56) fir_window8_c<56>(xs, ctaps, o, acc);
     else fir_window8(xs, tp, ntaps8, o, acc);
-    double sum = 0.0;
+    const double mean = p.dc_clip ? mean_s : 0.0;
 #pragma unroll
     for (int r = 0; r < kFirPer; r++) {
         const long long n = n0 + o + r;
         if (n < p.A) {
             double v = acc[r];
             if (p.deemph && n < K) v += p.zi[(long long)bc * K + n];
-            sum += v;
-            if (p.dc_clip) p.stage[(long long)bc * p.A + n] = v;
+            if (p.dc_clip) p.out[((long long)bq * p.A + n) * p.nch + chq] = epi_finish(p, v, mean);    // interleaved [A][nch]
             else p.out[(long long)bc * p.A + n] = (float)v;             // nch == 1 without mean removal
-        }
-    }
-    if (p.dc_clip) {
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-        if ((tid & 31) == 0) red[tid >> 5] = sum;
-        __syncthreads();
-        if (tid == 0) {
-            double t = 0.0;
-            for (int w = 0; w < kFirThreads / 32; w++) t += red[w];
-            p.partial[(long long)bc * nchunks + chunk] = t;
         }
     }
     if (p.deemph && chunk == nchunks - 1 && tid < K) {
         const int b = bc / p.nch, ch = bc - b * p.nch;
         p.zi_next[(long long)bc * K + tid] = epi_next_state(p, b, ch, tid);
-    }
-}
-
-// Phase 2: block mean over all nch*A samples of the channel, subtract, clip, interleave.
-static __global__ void __launch_bounds__(256) epi_finish_kernel(const EpilogueParams p, int nchunks) {
-    __shared__ double mean_s;
-    const int b = blockIdx.y, tid = threadIdx.x;
-    const long long total = p.A * p.nch;
-    if (tid < 32) {
-        double t = 0.0;
-        for (int i = tid; i < nchunks * p.nch; i += 32) t += p.partial[(long long)b * p.nch * nchunks + i];
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
-        if (tid == 0) mean_s = t / (double)total;
-    }
-    __syncthreads();
-    const double mean = mean_s;
-    for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(e % p.nch);
-        const long long n = e / p.nch;
-        p.out[(long long)b * total + e] = epi_finish(p, p.stage[((long long)b * p.nch + ch) * p.A + n], mean);
     }
 }
 
@@ -1025,13 +1029,29 @@ static __global__ void __launch_bounds__(kFirThreads) filtfilt_fold_kernel(const
 inline int epi_chunks(long long A) { return (int)((A + kFirChunk - 1) / kFirChunk); }
 
 // taps_host: the same ntaps float taps on the host (optional; enables the constant-operand FIR loop)
+inline FirSuffixParam fir_suffix_sums(const float* taps_host, int ntaps, bool deemph) {
+    FirSuffixParam sp;
+    memset(&sp, 0, sizeof(sp));
+    if (!deemph) { sp.c[0] = 1.0; return sp; }          // identity "filter": y = a
+    double acc = 0.0;
+    for (int m = ntaps - 1; m >= 0; m--) { acc += (double)taps_host[m]; sp.c[m] = acc; }
+    return sp;
+}
+
+// taps_host: the same ntaps float taps on the host (required with dc_clip; enables the constant-operand FIR loop)
 inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStream_t stream, const float* taps_host = nullptr) {
+    if (p.dc_clip && (!taps_host || !p.dc || p.ntaps > 56)) return cudaErrorInvalidValue;
+    const FirSuffixParam sp = taps_host ? fir_suffix_sums(taps_host, p.ntaps, p.deemph != 0) : FirSuffixParam{};
 #ifdef RC_EMULATE
     const long long total = p.A * p.nch;
     for (int b = 0; b < batch; b++) {
-        double sum = 0.0;
-        for (long long e = 0; e < total; e++) sum += epi_fir(p, b, (int)(e % p.nch), e / p.nch);
-        const double mean = sum / (double)total;
+        double mean = 0.0;
+        if (p.dc_clip) {
+            double sum = 0.0;
+            for (int ch = 0; ch < p.nch; ch++)
+                for (int lane = 0; lane < 32; lane++) sum += epi_channel_sum_lane(p, sp, (long long)b * p.nch + ch, lane, 32);
+            mean = sum / (double)total;
+        }
         if (p.deemph) {
             const int K = p.ntaps - 1;
             for (int e = 0; e < K * p.nch; e++)
@@ -1046,25 +1066,15 @@ inline cudaError_t launch_epilogue(const EpilogueParams& p, int batch, cudaStrea
     if (batch <= 0) return cudaSuccess;
     if (p.ntaps > kFirMaxTaps - 8 || (!p.dc_clip && p.nch != 1)) return cudaErrorInvalidValue;
     const int nchunks = epi_chunks(p.A);
-    {
-        ProfileScope scope("demod.deemph_fir", (4.0 + (p.dc_clip ? 8.0 : 4.0)) * (double)p.A * p.nch * batch, stream);
-        FirTapsParam ct;
-        memset(&ct, 0, sizeof(ct));
-        if (taps_host && p.deemph && p.ntaps > 48 && p.ntaps <= 56) {
-            const int K = p.ntaps - 1;
-            for (int i = 0; i <= K; i++) ct.t[i] = (double)taps_host[K - i];      // reversed, as in the kernel's table
-            ct.n8 = 56;
-        }
-        epi_fir_kernel<<<dim3((unsigned)nchunks, (unsigned)(batch * p.nch)), kFirThreads, 0, stream>>>(p, nchunks, ct);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+    ProfileScope scope(p.dc_clip ? "demod.deemph_mean_clip" : "demod.deemph_fir", 8.0 * (double)p.A * p.nch * batch, stream);
+    FirTapsParam ct;
+    memset(&ct, 0, sizeof(ct));
+    if (taps_host && p.deemph && p.ntaps > 48 && p.ntaps <= 56) {
+        const int K = p.ntaps - 1;
+        for (int i = 0; i <= K; i++) ct.t[i] = (double)taps_host[K - i];      // reversed, as in the kernel's table
+        ct.n8 = 56;
     }
-    if (p.dc_clip) {
-        ProfileScope scope("demod.mean_clip", 12.0 * (double)p.A * p.nch * batch, stream);
-        int gx = (int)((p.A * p.nch + 1023) / 1024);
-        if (gx < 1) gx = 1;
-        epi_finish_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, stream>>>(p, nchunks);
-    }
+    epi_fir_kernel<<<dim3((unsigned)nchunks, (unsigned)(batch * p.nch)), kFirThreads, 0, stream>>>(p, nchunks, ct, sp);
     return cudaGetLastError();
 #endif
 }
