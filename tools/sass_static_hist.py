@@ -20,7 +20,7 @@ FAMILIES = [("v3_first_kernel", "first FFT pass (fused loaders: TMA tile / tuner
             ("v3_later_kernel", "later FFT passes (fused stores: angle, window, lmr, peer scatter)"),
             ("fft_pass_kernel", "generic shared-memory pass (sizes without a register-radix split)"),
             ("ew_kernel", "elementwise functors (spectral resample / taper / Hilbert / stereo, sub-band combine)"),
-            ("epi_fir_kernel", "de-emphasis FIR"), ("epi_finish_kernel", "mean / clip"),
+            ("epi_fir_kernel", "de-emphasis FIR + block mean + clip"),
             ("filtfilt_fold_kernel", "folded pilot filter (fp32 pairs)"), ("filtfilt_kernel", "zero-phase FIR, exact fp64")]
 WATCH = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "DFMA", "DADD", "DMUL",
          "LDS", "STS", "LDG", "STG", "BAR", "MUFU", "F2F", "HMMA", "UTCHMMA", "UTCQMMA", "LDTM", "STTM", "ATOMG", "RED"]
